@@ -1,0 +1,105 @@
+"""Deterministic synthetic encoder weights and inputs (no network, no checkpoints).
+
+Keys and shapes are the reference encoder's state-dict contract
+(espnet/nets/pytorch_backend/encoder/conformer_encoder.py:212-262; 40 keys per
+layer + ``after_norm.{weight,bias}``).  Values are *not* the
+reference's default init: LayerNorm/BatchNorm affine, running statistics and all
+biases are non-trivial so that a kernel that drops one of them cannot pass parity
+(default init leaves them 0/1).
+
+Every tensor is drawn from its own ``torch.Generator`` seeded by (seed, key), so the
+same (seed, config) gives the same weights on any host with this torch build; the
+golden fixtures under ``tests/golden`` store only the seed.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from collections import OrderedDict
+from typing import Dict, Sequence
+
+import torch
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 63 - 1))
+    return g
+
+
+def encoder_state_dict(seed: int = 0, d_model: int = 768, n_heads: int = 12, linear_units: int = 3072,
+                       num_blocks: int = 12, cnn_kernel: int = 31,
+                       dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
+    """Synthetic ``ConformerEncoder.state_dict()`` in the reference's key order."""
+    dk = d_model // n_heads
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def uni(key, shape, bound):
+        sd[key] = (torch.rand(shape, generator=_gen(seed, key), dtype=torch.float64) * 2 - 1).mul_(bound).to(dtype)
+
+    def nrm(key, shape, std, mean=0.0):
+        sd[key] = (torch.randn(shape, generator=_gen(seed, key), dtype=torch.float64) * std + mean).to(dtype)
+
+    def pos(key, shape, lo, hi):
+        sd[key] = (torch.rand(shape, generator=_gen(seed, key), dtype=torch.float64) * (hi - lo) + lo).to(dtype)
+
+    def linear(pfx, out_f, in_f, bias=True):
+        uni(pfx + ".weight", (out_f, in_f), 1.0 / math.sqrt(in_f))
+        if bias:
+            nrm(pfx + ".bias", (out_f,), 0.1)
+
+    def lnorm(pfx):
+        pos(pfx + ".weight", (d_model,), 0.5, 1.5)
+        nrm(pfx + ".bias", (d_model,), 0.1)
+
+    for l in range(num_blocks):
+        p = f"encoders.{l}."
+        # key order == the reference module registration order (conformer_encoder.py:61-94)
+        uni(p + "self_attn.pos_bias_u", (n_heads, dk), math.sqrt(6.0 / (n_heads + dk)))
+        uni(p + "self_attn.pos_bias_v", (n_heads, dk), math.sqrt(6.0 / (n_heads + dk)))
+        linear(p + "self_attn.linear_q", d_model, d_model)
+        linear(p + "self_attn.linear_k", d_model, d_model)
+        linear(p + "self_attn.linear_v", d_model, d_model)
+        linear(p + "self_attn.linear_out", d_model, d_model)
+        linear(p + "self_attn.linear_pos", d_model, d_model, bias=False)
+        linear(p + "feed_forward.w_1", linear_units, d_model)
+        linear(p + "feed_forward.w_2", d_model, linear_units)
+        uni(p + "conv_module.pointwise_cov1.weight", (2 * d_model, d_model, 1), 1.0 / math.sqrt(d_model))
+        nrm(p + "conv_module.pointwise_cov1.bias", (2 * d_model,), 0.1)
+        uni(p + "conv_module.depthwise_conv.weight", (d_model, 1, cnn_kernel), 1.0 / math.sqrt(cnn_kernel))
+        nrm(p + "conv_module.depthwise_conv.bias", (d_model,), 0.1)
+        pos(p + "conv_module.norm.weight", (d_model,), 0.5, 1.5)
+        nrm(p + "conv_module.norm.bias", (d_model,), 0.1)
+        nrm(p + "conv_module.norm.running_mean", (d_model,), 0.1)
+        pos(p + "conv_module.norm.running_var", (d_model,), 0.5, 1.5)
+        sd[p + "conv_module.norm.num_batches_tracked"] = torch.tensor(100 + l, dtype=torch.long)
+        uni(p + "conv_module.pointwise_cov2.weight", (d_model, d_model, 1), 1.0 / math.sqrt(d_model))
+        nrm(p + "conv_module.pointwise_cov2.bias", (d_model,), 0.1)
+        lnorm(p + "norm_ff")
+        lnorm(p + "norm_mha")
+        linear(p + "feed_forward_macaron.w_1", linear_units, d_model)
+        linear(p + "feed_forward_macaron.w_2", d_model, linear_units)
+        lnorm(p + "norm_ff_macaron")
+        lnorm(p + "norm_conv")
+        lnorm(p + "norm_final")
+    lnorm("after_norm")
+    return sd
+
+
+def encoder_input(lengths: Sequence[int], d_model: int = 768, seed: int = 1234,
+                  dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """(B, Tmax, d) O(1)-scale frames; padded positions keep random values."""
+    B, T = len(lengths), max(int(v) for v in lengths)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return torch.randn(B, T, d_model, generator=g, dtype=torch.float64).to(dtype)
+
+
+#: Canonical length sets of SURVEY.md §8 (25 Hz frames).
+SHAPES: Dict[str, Sequence[int]] = {
+    "S1": [100],
+    "S2": [400] * 4,
+    "S2r": [400, 350, 300, 250, 300],
+    "S3": [100] * 16,
+    "S4": [1600],
+}
