@@ -1,0 +1,100 @@
+"""ctypes binding of libavsr_b200.so (include/avsr_b200.h).  No torch types cross this boundary:
+only raw device pointers, ints and sizes.  Importing this module without the built library raises --
+there is no CPU or PyTorch fallback for the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libavsr_b200.so")
+
+OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
+PREC_FP32, PREC_TF32 = 0, 1
+ABI_VERSION = 1
+
+
+class AvsrError(RuntimeError):
+    pass
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_heads", C.c_int32), ("linear_units", C.c_int32),
+                ("num_blocks", C.c_int32), ("cnn_kernel", C.c_int32)]
+
+
+#: field order of AvsrLayerParams (include/avsr_b200.h) -> reference state-dict key suffix
+LAYER_FIELDS = [
+    ("ffm_w1", "feed_forward_macaron.w_1.weight"), ("ffm_b1", "feed_forward_macaron.w_1.bias"),
+    ("ffm_w2", "feed_forward_macaron.w_2.weight"), ("ffm_b2", "feed_forward_macaron.w_2.bias"),
+    ("norm_ffm_w", "norm_ff_macaron.weight"), ("norm_ffm_b", "norm_ff_macaron.bias"),
+    ("q_w", "self_attn.linear_q.weight"), ("q_b", "self_attn.linear_q.bias"),
+    ("k_w", "self_attn.linear_k.weight"), ("k_b", "self_attn.linear_k.bias"),
+    ("v_w", "self_attn.linear_v.weight"), ("v_b", "self_attn.linear_v.bias"),
+    ("out_w", "self_attn.linear_out.weight"), ("out_b", "self_attn.linear_out.bias"),
+    ("pos_w", "self_attn.linear_pos.weight"),
+    ("pos_bias_u", "self_attn.pos_bias_u"), ("pos_bias_v", "self_attn.pos_bias_v"),
+    ("norm_mha_w", "norm_mha.weight"), ("norm_mha_b", "norm_mha.bias"),
+    ("pw1_w", "conv_module.pointwise_cov1.weight"), ("pw1_b", "conv_module.pointwise_cov1.bias"),
+    ("dw_w", "conv_module.depthwise_conv.weight"), ("dw_b", "conv_module.depthwise_conv.bias"),
+    ("bn_w", "conv_module.norm.weight"), ("bn_b", "conv_module.norm.bias"),
+    ("bn_mean", "conv_module.norm.running_mean"), ("bn_var", "conv_module.norm.running_var"),
+    ("pw2_w", "conv_module.pointwise_cov2.weight"), ("pw2_b", "conv_module.pointwise_cov2.bias"),
+    ("norm_conv_w", "norm_conv.weight"), ("norm_conv_b", "norm_conv.bias"),
+    ("ff_w1", "feed_forward.w_1.weight"), ("ff_b1", "feed_forward.w_1.bias"),
+    ("ff_w2", "feed_forward.w_2.weight"), ("ff_b2", "feed_forward.w_2.bias"),
+    ("norm_ff_w", "norm_ff.weight"), ("norm_ff_b", "norm_ff.bias"),
+    ("norm_final_w", "norm_final.weight"), ("norm_final_b", "norm_final.bias"),
+]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _ in LAYER_FIELDS]
+
+
+#: every symbol include/avsr_b200.h declares: name -> (restype, argtypes)
+_P, _I, _Z, _F = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+_CFG = C.POINTER(EncoderConfig)
+SIGNATURES = {
+    "avsr_abi_version": (_I, []),
+    "avsr_last_error": (C.c_char_p, []),
+    "avsr_launch_count": (C.c_uint64, []),
+    "avsr_prepared_bytes": (_Z, [_CFG]),
+    "avsr_prepare_weights": (_I, [_CFG, C.POINTER(LayerParams), _P, _P, _P, _Z, _I, _P]),
+    "avsr_workspace_bytes": (_Z, [_CFG, _I, _I]),
+    "avsr_encoder_forward": (_I, [_CFG, _P, _P, _P, _I, _I, _P, _P, _Z, _I, _P]),
+    "avsr_encoder_forward_taps": (_I, [_CFG, _P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
+    "avsr_plan_create": (_I, [_CFG, _P, _I, _I, _P, _Z, _I, _P, C.POINTER(_P)]),
+    "avsr_plan_forward": (_I, [_P, _P, _P, _P, _P]),
+    "avsr_plan_destroy": (None, [_P]),
+    "avsr_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "avsr_linear": (_I, [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _P]),
+    "avsr_attention_workspace_bytes": (_Z, [_I, _I, _I]),
+    "avsr_relpos_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "avsr_dwconv_bn_silu": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "avsr_pointwise_glu": (_I, [_P, _P, _P, _P, _I, _I, _P, _Z, _I, _P]),
+    "avsr_rel_sinusoid_table": (_I, [_P, _I, _I, _P]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  auto_avsr_b200 has no CPU / PyTorch fallback for the encoder hot path.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+if lib.avsr_abi_version() != ABI_VERSION:
+    raise ImportError(f"libavsr_b200 ABI {lib.avsr_abi_version()} != binding ABI {ABI_VERSION}")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = lib.avsr_last_error().decode("utf-8", "replace")
+        raise AvsrError(f"libavsr_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib.avsr_launch_count())

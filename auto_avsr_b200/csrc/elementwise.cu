@@ -1,0 +1,203 @@
+// HBM-bound kernels of the Conformer layer: embed scale, LayerNorm, rel-pos sinusoid table,
+// depthwise-conv + BatchNorm(eval) + SiLU.  fp32 math; coalesced float4 accesses along the channel axis
+// (channels are the contiguous axis of the reference's (B,T,C) layout, so a warp reads 512 contiguous bytes).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace avsr {
+
+// ------------------------------------------------------------------ embed: x = xs * sqrt(d)   (embedding.py:178)
+__global__ void embed_scale_kernel(const float4* __restrict__ xs, float4* __restrict__ x, long n4, float scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = xs[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    x[i] = v;
+  }
+}
+
+int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStream_t st) {
+  AVSR_REQUIRE(n % 4 == 0, "embed: element count %ld not a multiple of 4", n);
+  long n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  embed_scale_kernel<<<blocks, 256, 0, st>>>((const float4*)xs, (float4*)x, n4, scale);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ LayerNorm (layer_norm.py:21, eps 1e-12)
+// One warp per row; the row lives in registers (d <= 1024) so HBM sees exactly one read and one write.
+// Two-pass mean / centred variance, warp-shuffle reductions.
+constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ y,
+                                                        int rows, int d, int round_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
+  float4* yr = reinterpret_cast<float4*>(y + (long)warp * d);
+  const int nvec = d >> 2;
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      v[i] = xr[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      const float4 g = g4[c], b = b4[c];
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      yr[c] = o;
+    }
+  }
+}
+
+int launch_layernorm(const float* x, const float* g, const float* b, float* y, int rows, int d, int round_out,
+                     cudaStream_t st) {
+  AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
+               kLnMaxVec * 128);
+  if (rows <= 0) return AVSR_OK;
+  const int warps_per_block = 8;
+  layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, st>>>(x, g, b, y, rows, d, round_out);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ rel-pos sinusoid table (embedding.py:139-184)
+// Row m <-> rel = T-1-m; even channels sin(rel*w_i), odd channels cos(rel*w_i), w_i = exp(2i * -(ln 1e4 / d)).
+// The reference evaluates everything in fp32: the frequency is a correctly rounded fp32 exp, the
+// argument an fp32 product; sinf/cosf here take the full-range (non fast-math) path.
+__global__ void sinusoid_kernel(float* __restrict__ pe, int T, int d, int round_out) {
+  const int half = d >> 1;
+  const long total = (long)(2 * T - 1) * half;
+  const float step = (float)(-(log(10000.0) / (double)d));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / half), c = (int)(i - (long)m * half);
+    const float e = (float)(2 * c) * step;
+    const float inv = (float)exp((double)e);
+    const int rel = T - 1 - m;
+    float arg = fabsf((float)rel) * inv;
+    if (rel < 0) arg = -arg;
+    float s = sinf(arg), co = cosf(arg);
+    if (round_out) { s = round_tf32(s); co = round_tf32(co); }
+    reinterpret_cast<float2*>(pe + (long)m * d)[c] = make_float2(s, co);
+  }
+}
+
+int launch_sinusoid(float* pe, int T, int d, int round_out, cudaStream_t st) {
+  AVSR_REQUIRE(T > 0 && d > 0 && d % 2 == 0, "sinusoid: bad T=%d d=%d", T, d);
+  const long total = (long)(2 * T - 1) * (d / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sinusoid_kernel<<<blocks, 256, 0, st>>>(pe, T, d, round_out);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ depthwise conv + BN(eval) + SiLU
+// y[b,t,c] = silu( (sum_k wt[k][c] * x[b, t+k-half, c]) * scale[c] + shift[c] ),  x zero outside [0,T) per
+// utterance row b -- no length mask: padded frames are data (conformer_encoder.py:30-35).
+// scale/shift fold the depthwise bias and the BatchNorm running statistics (avsr_prepare_weights).
+// Tile: 64 channels x 32 frames per CTA; the (32+K-1) x 64 input patch and the K x 64 taps are staged in
+// shared memory with coalesced float4 loads; each thread produces 2 frames of one channel quad.
+constexpr int kDwCh = 64;
+constexpr int kDwTT = 32;
+
+__global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, float* __restrict__ y,
+                                                             int T, int C, int K, int round_out) {
+  extern __shared__ float4 dw_smem[];
+  const int rows_in = kDwTT + K - 1;
+  float4* in_s = dw_smem;                          // [rows_in][16]
+  float4* w_s = dw_smem + rows_in * (kDwCh / 4);   // [K][16]
+  const int c0 = blockIdx.x * kDwCh;
+  const int t0 = blockIdx.y * kDwTT;
+  const int b = blockIdx.z;
+  const int half = (K - 1) >> 1;
+  const int tid = threadIdx.x;
+  const float* xb = x + (long)b * T * C;
+
+  for (int i = tid; i < rows_in * (kDwCh / 4); i += 256) {
+    const int r = i >> 4, q = i & 15;
+    const int t = t0 - half + r, c = c0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T && c < C) v = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
+    in_s[i] = v;
+  }
+  for (int i = tid; i < K * (kDwCh / 4); i += 256) {
+    const int k = i >> 4, q = i & 15;
+    const int c = c0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) v = *reinterpret_cast<const float4*>(wt + (long)k * C + c);
+    w_s[i] = v;
+  }
+  __syncthreads();
+
+  const int q = tid & 15, ts = tid >> 4;
+  const int c = c0 + q * 4;
+  if (c >= C) return;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+  const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  for (int k = 0; k < K; ++k) {
+    const float4 w = w_s[k * 16 + q];
+    const float4 u0 = in_s[(ts + k) * 16 + q];
+    const float4 u1 = in_s[(ts + 16 + k) * 16 + q];
+    a0.x = fmaf(w.x, u0.x, a0.x); a0.y = fmaf(w.y, u0.y, a0.y); a0.z = fmaf(w.z, u0.z, a0.z); a0.w = fmaf(w.w, u0.w, a0.w);
+    a1.x = fmaf(w.x, u1.x, a1.x); a1.y = fmaf(w.y, u1.y, a1.y); a1.z = fmaf(w.z, u1.z, a1.z); a1.w = fmaf(w.w, u1.w, a1.w);
+  }
+  auto finish = [&](float4 a, int t) {
+    if (t >= T) return;
+    float4 o;
+    o.x = fmaf(a.x, sc.x, sh.x); o.y = fmaf(a.y, sc.y, sh.y); o.z = fmaf(a.z, sc.z, sh.z); o.w = fmaf(a.w, sc.w, sh.w);
+    o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
+    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    *reinterpret_cast<float4*>(y + ((long)b * T + t) * C + c) = o;
+  };
+  finish(a0, t0 + ts);
+  finish(a1, t0 + ts + 16);
+}
+
+int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, float* y, int B,
+                          int T, int C, int K, int round_out, cudaStream_t st) {
+  AVSR_REQUIRE(C % 4 == 0 && K % 2 == 1 && K >= 1 && K <= 255, "dwconv: C=%d must be a multiple of 4, K=%d odd", C, K);
+  if (B <= 0 || T <= 0) return AVSR_OK;
+  const size_t smem = (size_t)(kDwTT + K - 1 + K) * (kDwCh / 4) * sizeof(float4);
+  if (smem > 48 * 1024)
+    AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(C, kDwCh), cdiv(T, kDwTT), B);
+  dwconv_bn_silu_kernel<<<grid, 256, smem, st>>>(x, wt, scale, shift, y, T, C, K, round_out);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+}  // namespace avsr

@@ -1,0 +1,536 @@
+// Host orchestration + C ABI of libavsr_b200: weight preparation, workspace carving, the 12-layer
+// forward schedule (ConformerEncoder.forward, conformer_encoder.py:264-282) and the CUDA-graph plan.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace avsr {
+
+// ------------------------------------------------------------------ error / accounting
+static thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+// ------------------------------------------------------------------ prepared-weight layout
+struct LayerPrep {
+  float *ffm_w1, *ffm_b1, *ffm_w2, *ffm_b2, *ln_ffm_w, *ln_ffm_b;
+  float *qk_w, *qk_b, *v_w, *v_b, *out_w, *out_b, *pos_u, *pos_v, *ln_mha_w, *ln_mha_b;
+  float *pw1_w, *pw1_b, *dw_wt, *dw_scale, *dw_shift, *pw2_w, *pw2_b, *ln_conv_w, *ln_conv_b;
+  float *ff_w1, *ff_b1, *ff_w2, *ff_b2, *ln_ff_w, *ln_ff_b;
+  float *ln_fin_w, *ln_fin_b;
+};
+struct Prepared {
+  std::vector<LayerPrep> layers;
+  float *pos_w_all, *after_w, *after_b;
+  size_t bytes;
+};
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  float* take(size_t nfloats) {
+    float* p = reinterpret_cast<float*>(base + off);
+    off += align_up(nfloats * sizeof(float), 256);
+    return p;
+  }
+};
+
+static Prepared layout_prepared(const AvsrEncoderConfig& c, void* base) {
+  Prepared P;
+  Carver cv{reinterpret_cast<char*>(base)};
+  const size_t D = c.d_model, F = c.linear_units, K = c.cnn_kernel;
+  P.layers.resize(c.num_blocks);
+  for (auto& L : P.layers) {
+    L.ffm_w1 = cv.take(F * D); L.ffm_b1 = cv.take(F); L.ffm_w2 = cv.take(D * F); L.ffm_b2 = cv.take(D);
+    L.ln_ffm_w = cv.take(D); L.ln_ffm_b = cv.take(D);
+    L.qk_w = cv.take(2 * D * D); L.qk_b = cv.take(2 * D); L.v_w = cv.take(D * D); L.v_b = cv.take(D);
+    L.out_w = cv.take(D * D); L.out_b = cv.take(D); L.pos_u = cv.take(D); L.pos_v = cv.take(D);
+    L.ln_mha_w = cv.take(D); L.ln_mha_b = cv.take(D);
+    L.pw1_w = cv.take(2 * D * D); L.pw1_b = cv.take(2 * D); L.dw_wt = cv.take(K * D);
+    L.dw_scale = cv.take(D); L.dw_shift = cv.take(D); L.pw2_w = cv.take(D * D); L.pw2_b = cv.take(D);
+    L.ln_conv_w = cv.take(D); L.ln_conv_b = cv.take(D);
+    L.ff_w1 = cv.take(F * D); L.ff_b1 = cv.take(F); L.ff_w2 = cv.take(D * F); L.ff_b2 = cv.take(D);
+    L.ln_ff_w = cv.take(D); L.ln_ff_b = cv.take(D);
+    L.ln_fin_w = cv.take(D); L.ln_fin_b = cv.take(D);
+  }
+  P.pos_w_all = cv.take((size_t)c.num_blocks * D * D);
+  P.after_w = cv.take(D);
+  P.after_b = cv.take(D);
+  P.bytes = cv.off;
+  return P;
+}
+
+static int check_cfg(const AvsrEncoderConfig* c) {
+  AVSR_REQUIRE(c != nullptr, "config is NULL");
+  AVSR_REQUIRE(c->n_heads > 0 && c->d_model == c->n_heads * kHeadDim,
+               "d_model=%d must be n_heads=%d * 64 (the attention kernels are built for d_k = 64)", c->d_model,
+               c->n_heads);
+  AVSR_REQUIRE(c->d_model % 64 == 0 && c->d_model <= 1024, "d_model=%d must be a multiple of 64 and <= 1024", c->d_model);
+  AVSR_REQUIRE(c->linear_units > 0 && c->linear_units % 64 == 0, "linear_units=%d must be a multiple of 64",
+               c->linear_units);
+  AVSR_REQUIRE(c->num_blocks > 0, "num_blocks=%d", c->num_blocks);
+  AVSR_REQUIRE(c->cnn_kernel % 2 == 1 && c->cnn_kernel >= 1 && c->cnn_kernel <= 255, "cnn_kernel=%d must be odd",
+               c->cnn_kernel);
+  return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ preparation kernels
+__global__ void copy_round_kernel(const float* __restrict__ src, float* __restrict__ dst, long n, int round_out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    dst[i] = round_out ? round_tf32(v) : v;
+  }
+}
+// pointwise_cov1 (2D, D[,1]) -> rows interleaved in groups of 64: [g*128, +64) value channels g*64.., then their gates
+__global__ void glu_interleave_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wo,
+                                      float* __restrict__ bo, int D, int round_out) {
+  const int r = blockIdx.x;  // destination row in [0, 2D)
+  const int g = r >> 7, wi = r & 127;
+  const int src = wi < 64 ? g * 64 + wi : D + g * 64 + (wi - 64);
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    const float v = w[(long)src * D + k];
+    wo[(long)r * D + k] = round_out ? round_tf32(v) : v;
+  }
+  if (threadIdx.x == 0) bo[r] = b[src];
+}
+// depthwise taps (C,1,K) -> (K,C); BN(eval)+conv bias folded: scale = g/sqrt(var+eps), shift = beta + (b - mean)*scale
+__global__ void dw_fold_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ bn_w,
+                               const float* __restrict__ bn_b, const float* __restrict__ mean,
+                               const float* __restrict__ var, float* __restrict__ wt, float* __restrict__ scale,
+                               float* __restrict__ shift, int C, int K) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int k = 0; k < K; ++k) wt[(long)k * C + c] = w[(long)c * K + k];
+  const float s = bn_w[c] / sqrtf(var[c] + 1e-5f);
+  scale[c] = s;
+  shift[c] = bn_b[c] + (b[c] - mean[c]) * s;
+}
+
+static int copy_round(const float* src, float* dst, long n, int round_out, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  copy_round_kernel<<<blocks, 256, 0, st>>>(src, dst, n, round_out);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Workspace {
+  float *x, *xn, *hid, *qu, *qv, *kk, *vt, *ctx, *glu, *dw, *pe, *pos;
+  int32_t* lengths;
+  int Tp, Rp;
+  size_t bytes;
+};
+
+static Workspace layout_workspace(const AvsrEncoderConfig& c, int B, int T, void* base) {
+  Workspace W;
+  Carver cv{reinterpret_cast<char*>(base)};
+  const size_t N = (size_t)B * T, D = c.d_model, F = c.linear_units;
+  W.Tp = (T + 3) & ~3;
+  W.Rp = 2 * T - 1;
+  W.x = cv.take(N * D); W.xn = cv.take(N * D); W.hid = cv.take(N * F);
+  W.qu = cv.take(N * D); W.qv = cv.take(N * D); W.kk = cv.take(N * D);
+  W.vt = cv.take((size_t)B * D * W.Tp);
+  W.ctx = cv.take(N * D); W.glu = cv.take(N * D); W.dw = cv.take(N * D);
+  W.pe = cv.take((size_t)W.Rp * D);
+  W.pos = cv.take((size_t)c.num_blocks * W.Rp * D);
+  W.lengths = reinterpret_cast<int32_t*>(cv.take((size_t)B));
+  W.bytes = cv.off;
+  return W;
+}
+
+__global__ void fill_lengths_kernel(int32_t* dst, const int32_t* src, int B, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) dst[i] = src ? src[i] : T;
+}
+
+// ------------------------------------------------------------------ forward schedule
+static EpiParams epi_linear(int M, int N, const float* bias, float* out, const float* resid, float alpha, int relu,
+                            int round_out) {
+  EpiParams e{};
+  e.M = M; e.N = N; e.bias = bias; e.out = out; e.ldo = N; e.resid = resid; e.alpha = alpha; e.relu = relu;
+  e.round_out = round_out;
+  return e;
+}
+
+static int run_gemm(int prec, int mode, const float* A, const float* Bw, int M, int N, int K, const EpiParams& e,
+                    cudaStream_t st) {
+  return prec == AVSR_PREC_TF32 ? gemm_tc(mode, A, Bw, M, N, K, e, st) : gemm_simt(mode, A, Bw, M, N, K, e, st);
+}
+
+// the part of the forward that only touches workspace buffers (what a plan captures into its graph)
+static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int B, int T,
+                        const int32_t* lengths, float* taps, int prec, cudaStream_t st) {
+  const int N = B * T, D = c.d_model, F = c.linear_units, H = c.n_heads, L = c.num_blocks;
+  const int rnd = prec == AVSR_PREC_TF32 ? 1 : 0;
+  const size_t stage_bytes = (size_t)N * D * sizeof(float);
+
+  // pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
+  AVSR_TRY(launch_sinusoid(W.pe, T, D, rnd, st));
+  {
+    EpiParams e{};
+    e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = rnd;
+    AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, st));
+  }
+  if (W.Tp != T) AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
+
+  for (int l = 0; l < L; ++l) {
+    const LayerPrep& w = P.layers[l];
+    auto tap = [&](int s) -> int {
+      if (l == 0 && taps)
+        AVSR_CUDA_TRY(cudaMemcpyAsync(taps + (size_t)s * N * D, W.x, stage_bytes, cudaMemcpyDeviceToDevice, st));
+      return AVSR_OK;
+    };
+    // (1) macaron FFN: x += 0.5 * w2(relu(w1 LN(x)))                         conformer_encoder.py:110-116
+    AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, rnd, st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, rnd), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_linear(N, D, w.ffm_b2, W.x, W.x, 0.5f, 0, 0), st));
+    AVSR_TRY(tap(0));
+    // (2) rel-pos MHA: x += out(attn(LN(x)))                                  conformer_encoder.py:119-142
+    AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, rnd, st));
+    {
+      EpiParams e{};
+      e.M = N; e.N = 2 * D; e.bias = w.qk_b; e.T = T; e.H = H; e.pos_u = w.pos_u; e.pos_v = w.pos_v;
+      e.qu = W.qu; e.qv = W.qv; e.kk = W.kk; e.round_out = rnd;
+      AVSR_TRY(run_gemm(prec, EPI_QK, W.xn, w.qk_w, N, 2 * D, D, e, st));
+      EpiParams v{};
+      v.M = D; v.N = N; v.bias = w.v_b; v.T = T; v.H = H; v.Tp = W.Tp; v.vt = W.vt; v.round_out = rnd;
+      AVSR_TRY(run_gemm(prec, EPI_VT, w.v_w, W.xn, D, N, D, v, st));
+    }
+    {
+      const float* pos_l = W.pos + (size_t)l * H * W.Rp * kHeadDim;
+      if (prec == AVSR_PREC_TF32)
+        AVSR_TRY(attention_tc(W.qu, W.qv, W.kk, W.vt, pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, rnd, st));
+      else
+        AVSR_TRY(attention_simt(W.qu, W.qv, W.kk, W.vt, pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, rnd, st));
+    }
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.ctx, w.out_w, N, D, D, epi_linear(N, D, w.out_b, W.x, W.x, 1.0f, 0, 0), st));
+    AVSR_TRY(tap(1));
+    // (3) conv module: x += pw2(silu(bn(dw(glu(pw1 LN(x))))))                 conformer_encoder.py:145-151, :30-35
+    AVSR_TRY(launch_layernorm(W.x, w.ln_conv_w, w.ln_conv_b, W.xn, N, D, rnd, st));
+    {
+      EpiParams e{};
+      e.M = N; e.N = 2 * D; e.bias = w.pw1_b; e.out = W.glu; e.ldo = D;
+      AVSR_TRY(run_gemm(prec, EPI_GLU, W.xn, w.pw1_w, N, 2 * D, D, e, st));
+    }
+    AVSR_TRY(launch_dwconv_bn_silu(W.glu, w.dw_wt, w.dw_scale, w.dw_shift, W.dw, B, T, D, c.cnn_kernel, rnd, st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.dw, w.pw2_w, N, D, D, epi_linear(N, D, w.pw2_b, W.x, W.x, 1.0f, 0, 0), st));
+    AVSR_TRY(tap(2));
+    // (4) FFN: x += 0.5 * w2(relu(w1 LN(x)))                                  conformer_encoder.py:154-159
+    AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, rnd, st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, rnd), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_linear(N, D, w.ff_b2, W.x, W.x, 0.5f, 0, 0), st));
+    AVSR_TRY(tap(3));
+    // (5) x = LN_final(x)                                                     conformer_encoder.py:161-162
+    AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, 0, st));
+    AVSR_TRY(tap(4));
+  }
+  return AVSR_OK;
+}
+
+static int forward_impl(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs, const int32_t* lengths,
+                        int B, int T, float* out, float* taps, void* workspace, size_t workspace_bytes, int precision,
+                        void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(B >= 0 && T >= 0, "bad B=%d T=%d", B, T);
+  if (B == 0 || T == 0) return AVSR_OK;  // empty batch: nothing to do
+  AVSR_REQUIRE(prepared && xs && out && workspace, "NULL buffer");
+  AVSR_REQUIRE((long)B * T < (1L << 24), "B*T=%ld too large", (long)B * T);
+  Workspace W = layout_workspace(*cfg, B, T, workspace);
+  if (W.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", W.bytes, workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  Prepared P = layout_prepared(*cfg, const_cast<void*>(prepared));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  AVSR_TRY(launch_embed_scale(xs, W.x, (long)B * T * cfg->d_model, sqrtf((float)cfg->d_model), st));
+  AVSR_TRY(forward_body(*cfg, P, W, B, T, lengths, taps, precision, st));
+  AVSR_TRY(launch_layernorm(W.x, P.after_w, P.after_b, out, B * T, cfg->d_model, 0, st));
+  return AVSR_OK;
+}
+
+}  // namespace avsr
+
+// ====================================================================== C ABI
+using namespace avsr;
+
+struct AvsrPlan {
+  AvsrEncoderConfig cfg;
+  Prepared P;
+  Workspace W;
+  int B, T, precision;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" {
+
+int avsr_abi_version(void) { return AVSR_ABI_VERSION; }
+const char* avsr_last_error(void) { return g_err.c_str(); }
+uint64_t avsr_launch_count(void) { return g_launches.load(); }
+
+size_t avsr_prepared_bytes(const AvsrEncoderConfig* cfg) {
+  if (check_cfg(cfg) != AVSR_OK) return 0;
+  return layout_prepared(*cfg, nullptr).bytes;
+}
+
+int avsr_prepare_weights(const AvsrEncoderConfig* cfg, const AvsrLayerParams* layers, const float* after_norm_w,
+                         const float* after_norm_b, void* prepared, size_t prepared_bytes, int precision,
+                         void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(layers && after_norm_w && after_norm_b && prepared, "NULL argument");
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  Prepared P = layout_prepared(*cfg, prepared);
+  if (P.bytes > prepared_bytes) {
+    set_error("prepared buffer too small: need %zu bytes, got %zu", P.bytes, prepared_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rnd = precision == AVSR_PREC_TF32;
+  const long D = cfg->d_model, F = cfg->linear_units, K = cfg->cnn_kernel;
+  for (int l = 0; l < cfg->num_blocks; ++l) {
+    const AvsrLayerParams& s = layers[l];
+    const LayerPrep& d = P.layers[l];
+    const float* const* sp = reinterpret_cast<const float* const*>(&s);
+    for (size_t i = 0; i < sizeof(AvsrLayerParams) / sizeof(float*); ++i)
+      AVSR_REQUIRE(sp[i] != nullptr, "layer %d: parameter pointer #%zu is NULL", l, i);
+    AVSR_TRY(copy_round(s.ffm_w1, d.ffm_w1, F * D, rnd, st)); AVSR_TRY(copy_round(s.ffm_b1, d.ffm_b1, F, 0, st));
+    AVSR_TRY(copy_round(s.ffm_w2, d.ffm_w2, D * F, rnd, st)); AVSR_TRY(copy_round(s.ffm_b2, d.ffm_b2, D, 0, st));
+    AVSR_TRY(copy_round(s.norm_ffm_w, d.ln_ffm_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_ffm_b, d.ln_ffm_b, D, 0, st));
+    AVSR_TRY(copy_round(s.q_w, d.qk_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.k_w, d.qk_w + D * D, D * D, rnd, st));
+    AVSR_TRY(copy_round(s.q_b, d.qk_b, D, 0, st)); AVSR_TRY(copy_round(s.k_b, d.qk_b + D, D, 0, st));
+    AVSR_TRY(copy_round(s.v_w, d.v_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.v_b, d.v_b, D, 0, st));
+    AVSR_TRY(copy_round(s.out_w, d.out_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.out_b, d.out_b, D, 0, st));
+    AVSR_TRY(copy_round(s.pos_bias_u, d.pos_u, D, 0, st)); AVSR_TRY(copy_round(s.pos_bias_v, d.pos_v, D, 0, st));
+    AVSR_TRY(copy_round(s.norm_mha_w, d.ln_mha_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_mha_b, d.ln_mha_b, D, 0, st));
+    glu_interleave_kernel<<<(unsigned)(2 * D), 256, 0, st>>>(s.pw1_w, s.pw1_b, d.pw1_w, d.pw1_b, (int)D, rnd);
+    AVSR_CHECK_LAUNCH();
+    dw_fold_kernel<<<cdiv((int)D, 128), 128, 0, st>>>(s.dw_w, s.dw_b, s.bn_w, s.bn_b, s.bn_mean, s.bn_var, d.dw_wt,
+                                                      d.dw_scale, d.dw_shift, (int)D, (int)K);
+    AVSR_CHECK_LAUNCH();
+    AVSR_TRY(copy_round(s.pw2_w, d.pw2_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.pw2_b, d.pw2_b, D, 0, st));
+    AVSR_TRY(copy_round(s.norm_conv_w, d.ln_conv_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_conv_b, d.ln_conv_b, D, 0, st));
+    AVSR_TRY(copy_round(s.ff_w1, d.ff_w1, F * D, rnd, st)); AVSR_TRY(copy_round(s.ff_b1, d.ff_b1, F, 0, st));
+    AVSR_TRY(copy_round(s.ff_w2, d.ff_w2, D * F, rnd, st)); AVSR_TRY(copy_round(s.ff_b2, d.ff_b2, D, 0, st));
+    AVSR_TRY(copy_round(s.norm_ff_w, d.ln_ff_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_ff_b, d.ln_ff_b, D, 0, st));
+    AVSR_TRY(copy_round(s.norm_final_w, d.ln_fin_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_final_b, d.ln_fin_b, D, 0, st));
+    AVSR_TRY(copy_round(s.pos_w, P.pos_w_all + (size_t)l * D * D, D * D, rnd, st));
+  }
+  AVSR_TRY(copy_round(after_norm_w, P.after_w, D, 0, st));
+  AVSR_TRY(copy_round(after_norm_b, P.after_b, D, 0, st));
+  return AVSR_OK;
+}
+
+size_t avsr_workspace_bytes(const AvsrEncoderConfig* cfg, int B, int T) {
+  if (check_cfg(cfg) != AVSR_OK || B < 0 || T < 0) return 0;
+  if (B == 0 || T == 0) return 256;
+  return layout_workspace(*cfg, B, T, nullptr).bytes;
+}
+
+int avsr_encoder_forward(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs, const int32_t* lengths,
+                         int B, int T, float* out, void* workspace, size_t workspace_bytes, int precision,
+                         void* stream) {
+  return forward_impl(cfg, prepared, xs, lengths, B, T, out, nullptr, workspace, workspace_bytes, precision, stream);
+}
+
+int avsr_encoder_forward_taps(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs,
+                              const int32_t* lengths, int B, int T, float* out, float* taps, void* workspace,
+                              size_t workspace_bytes, int precision, void* stream) {
+  return forward_impl(cfg, prepared, xs, lengths, B, T, out, taps, workspace, workspace_bytes, precision, stream);
+}
+
+int avsr_plan_create(const AvsrEncoderConfig* cfg, const void* prepared, int B, int T, void* workspace,
+                     size_t workspace_bytes, int precision, void* stream, AvsrPlan** plan) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(plan && prepared && workspace, "NULL argument");
+  AVSR_REQUIRE(B > 0 && T > 0, "plan needs B>0, T>0 (got %d, %d)", B, T);
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  Workspace W = layout_workspace(*cfg, B, T, workspace);
+  if (W.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", W.bytes, workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  AvsrPlan* p = new AvsrPlan();
+  p->cfg = *cfg; p->B = B; p->T = T; p->precision = precision; p->W = W;
+  p->P = layout_prepared(*cfg, const_cast<void*>(prepared));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // warm-up outside capture: sets function attributes (dynamic smem opt-in) that capture must not do lazily
+  fill_lengths_kernel<<<cdiv(B, 128), 128, 0, st>>>(W.lengths, nullptr, B, T);
+  g_launches.fetch_add(1);
+  int rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st);
+  if (rc == AVSR_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("plan warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = AVSR_E_CUDA;
+  }
+  if (rc != AVSR_OK) { delete p; return rc; }
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); delete p; return AVSR_E_CUDA; }
+  const uint64_t before = g_launches.load();
+  rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st);
+  g_launches.store(before);  // captured launches are counted when the graph is replayed
+  e = cudaStreamEndCapture(st, &p->graph);
+  if (rc != AVSR_OK) { if (p->graph) cudaGraphDestroy(p->graph); delete p; return rc; }
+  if (e != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); delete p; return AVSR_E_CUDA; }
+  e = cudaGraphInstantiate(&p->exec, p->graph, 0);
+  if (e != cudaSuccess) {
+    set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    cudaGraphDestroy(p->graph); delete p; return AVSR_E_CUDA;
+  }
+  *plan = p;
+  return AVSR_OK;
+}
+
+static uint64_t graph_kernel_nodes(cudaGraph_t g) {
+  size_t n = 0;
+  if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess) return 0;
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n == 0 || cudaGraphGetNodes(g, nodes.data(), &n) != cudaSuccess) return 0;
+  uint64_t k = 0;
+  for (auto nd : nodes) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++k;
+  }
+  return k;
+}
+
+int avsr_plan_forward(AvsrPlan* p, const float* xs, const int32_t* lengths, float* out, void* stream) {
+  AVSR_REQUIRE(p && xs && out, "NULL argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int N = p->B * p->T, D = p->cfg.d_model;
+  fill_lengths_kernel<<<cdiv(p->B, 128), 128, 0, st>>>(p->W.lengths, lengths, p->B, p->T);
+  AVSR_CHECK_LAUNCH();
+  AVSR_TRY(launch_embed_scale(xs, p->W.x, (long)N * D, sqrtf((float)D), st));
+  AVSR_CUDA_TRY(cudaGraphLaunch(p->exec, st));
+  static thread_local cudaGraph_t counted = nullptr;
+  static thread_local uint64_t nk = 0;
+  if (counted != p->graph) { nk = graph_kernel_nodes(p->graph); counted = p->graph; }
+  g_launches.fetch_add(nk);
+  AVSR_TRY(launch_layernorm(p->W.x, p->P.after_w, p->P.after_b, out, N, D, 0, st));
+  return AVSR_OK;
+}
+
+void avsr_plan_destroy(AvsrPlan* p) {
+  if (!p) return;
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->graph) cudaGraphDestroy(p->graph);
+  delete p;
+}
+
+// ---------------------------------------------------------------------- per-op entry points
+int avsr_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, int d, void* stream) {
+  AVSR_REQUIRE(x && gamma && beta && y, "NULL argument");
+  return launch_layernorm(x, gamma, beta, y, rows, d, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int avsr_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int relu, float* y,
+                int rows, int n, int k, int precision, void* stream) {
+  AVSR_REQUIRE(x && w && y, "NULL argument");
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  // note: in TF32 mode operands are used as given (the tensor core truncates fp32 -> tf32)
+  return run_gemm(precision, EPI_LINEAR, x, w, rows, n, k, epi_linear(rows, n, bias, y, resid, alpha, relu, 0),
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+// (B,T,H*64) -> (B,H,T,64) with optional per-channel bias add; or -> (B,H,64,Tp) when transpose != 0
+__global__ void split_heads_kernel(const float* __restrict__ src, const float* __restrict__ bias, float* __restrict__ dst,
+                                   int B, int T, int H, int Tp, int transpose, int round_out) {
+  const long total = (long)B * T * H * kHeadDim;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (H * kHeadDim));
+    const long r = i / (H * kHeadDim);
+    const int b = (int)(r / T), t = (int)(r % T), h = c / kHeadDim, d = c % kHeadDim;
+    float v = src[i] + (bias ? bias[c] : 0.f);
+    if (round_out) v = round_tf32(v);
+    if (transpose) dst[(((long)b * H + h) * kHeadDim + d) * Tp + t] = v;
+    else dst[(((long)b * H + h) * T + t) * kHeadDim + d] = v;
+  }
+}
+
+size_t avsr_attention_workspace_bytes(int B, int T, int H) {
+  if (B <= 0 || T <= 0 || H <= 0) return 256;
+  const size_t N = (size_t)B * T, D = (size_t)H * kHeadDim, Tp = (T + 3) & ~3;
+  return 3 * align_up(N * D * 4, 256) + align_up((size_t)B * D * Tp * 4, 256) + align_up((size_t)(2 * T - 1) * D * 4, 256);
+}
+
+int avsr_relpos_attention(const float* q, const float* k, const float* v, const float* p, const float* pos_bias_u,
+                          const float* pos_bias_v, const int32_t* lengths, float* ctx, int B, int T, int H,
+                          void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  AVSR_REQUIRE(q && k && v && p && pos_bias_u && pos_bias_v && ctx && workspace, "NULL argument");
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  if (B <= 0 || T <= 0) return AVSR_OK;
+  if (avsr_attention_workspace_bytes(B, T, H) > workspace_bytes) {
+    set_error("attention workspace too small: need %zu, got %zu", avsr_attention_workspace_bytes(B, T, H), workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)B * T, D = (size_t)H * kHeadDim;
+  const int Tp = (T + 3) & ~3, R = 2 * T - 1;
+  const int rnd = precision == AVSR_PREC_TF32;
+  Carver cv{reinterpret_cast<char*>(workspace)};
+  float *qu = cv.take(N * D), *qv = cv.take(N * D), *kk = cv.take(N * D), *vt = cv.take((size_t)B * D * Tp),
+        *pos = cv.take((size_t)R * D);
+  const int blocks = 148 * 4;
+  if (Tp != T) AVSR_CUDA_TRY(cudaMemsetAsync(vt, 0, (size_t)B * D * Tp * sizeof(float), st));
+  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_u, qu, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_v, qv, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(k, nullptr, kk, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(v, nullptr, vt, B, T, H, Tp, 1, rnd); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(p, nullptr, pos, 1, R, H, R, 0, rnd); AVSR_CHECK_LAUNCH();
+  if (rnd) return attention_tc(qu, qv, kk, vt, pos, lengths, ctx, B, T, H, Tp, R, 0, st);
+  return attention_simt(qu, qv, kk, vt, pos, lengths, ctx, B, T, H, Tp, R, 0, st);
+}
+
+int avsr_dwconv_bn_silu(const float* x, const float* w, const float* b, const float* bn_w, const float* bn_b,
+                        const float* bn_mean, const float* bn_var, float* y, int B, int T, int C, int K,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  AVSR_REQUIRE(x && w && b && bn_w && bn_b && bn_mean && bn_var && y && workspace, "NULL argument");
+  AVSR_REQUIRE(C > 0 && C % 4 == 0 && K >= 1 && K % 2 == 1, "dwconv: bad C=%d K=%d", C, K);
+  if ((size_t)(K + 2) * C * sizeof(float) > workspace_bytes) {
+    set_error("dwconv workspace too small: need %zu bytes, got %zu", (size_t)(K + 2) * C * sizeof(float), workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *wt = reinterpret_cast<float*>(workspace), *scale = wt + (size_t)K * C, *shift = scale + C;
+  dw_fold_kernel<<<cdiv(C, 128), 128, 0, st>>>(w, b, bn_w, bn_b, bn_mean, bn_var, wt, scale, shift, C, K);
+  AVSR_CHECK_LAUNCH();
+  return launch_dwconv_bn_silu(x, wt, scale, shift, y, B, T, C, K, 0, st);
+}
+
+int avsr_pointwise_glu(const float* x, const float* w, const float* b, float* y, int rows, int C, void* workspace,
+                       size_t workspace_bytes, int precision, void* stream) {
+  AVSR_REQUIRE(x && w && b && y && workspace, "NULL argument");
+  AVSR_REQUIRE(C > 0 && C % 64 == 0, "pointwise_glu: C=%d must be a multiple of 64", C);
+  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  const size_t need = ((size_t)2 * C * C + 2 * C) * sizeof(float);
+  if (need > workspace_bytes) {
+    set_error("pointwise_glu workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *wi = reinterpret_cast<float*>(workspace), *bi = wi + (size_t)2 * C * C;
+  glu_interleave_kernel<<<(unsigned)(2 * C), 256, 0, st>>>(w, b, wi, bi, C, 0);
+  AVSR_CHECK_LAUNCH();
+  EpiParams e{};
+  e.M = rows; e.N = 2 * C; e.bias = bi; e.out = y; e.ldo = C;
+  return run_gemm(precision, EPI_GLU, x, wi, rows, 2 * C, C, e, st);
+}
+
+int avsr_rel_sinusoid_table(float* pe, int T, int d, void* stream) {
+  AVSR_REQUIRE(pe, "NULL argument");
+  return launch_sinusoid(pe, T, d, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+/*
+ * avsr_b200.h -- C ABI of libavsr_b200.so: the B200 (sm_100a) Conformer-encoder forward path.
+ *
+ * The reference (mpc001/auto_avsr @ 182b628) has no FFI layer: its boundary for this path is the
+ * Python nn.Module surface.  These entry points are what a binding for that
+ * surface needs; auto_avsr_b200/_cabi.py binds them with ctypes and the modules in
+ * auto_avsr_b200/espnet_dropin/ call them.  Each entry names the reference interface it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers (unless a parameter says host), ints, sizes.
+ *   - the caller owns every buffer (inputs, outputs, prepared weights, workspace); the library never
+ *     allocates device memory and keeps no global device state.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 = success, non-zero = AVSR_E_*; avsr_last_error() gives the message
+ *     (thread-local, valid until the next call on that thread).
+ *   - all float tensors are fp32, contiguous, row-major; "frames" are rows r = b*T + t.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with AVSR_E_CUDA.
+ */
+#ifndef AVSR_B200_H_
+#define AVSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVSR_ABI_VERSION 1
+
+enum {
+  AVSR_OK = 0,
+  AVSR_E_INVALID = 1,   /* bad argument / unsupported shape */
+  AVSR_E_CUDA = 2,      /* CUDA runtime / driver error (message has the CUDA error string) */
+  AVSR_E_WORKSPACE = 3  /* workspace or prepared-weight buffer too small */
+};
+
+/* Arithmetic of the GEMM / attention contractions. */
+enum {
+  AVSR_PREC_FP32 = 0,  /* CUDA-core fp32 FMA kernels: the on-device exact reference path (slow) */
+  AVSR_PREC_TF32 = 1   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate (the product path) */
+};
+
+/* Hyper-parameters hard-wired in E2E.__init__ (espnet/nets/pytorch_backend/e2e_asr_conformer.py:33-39):
+ * d_model 768, n_heads 12, linear_units 3072, num_blocks 12, cnn_kernel 31.  d_model/n_heads must be 64. */
+typedef struct AvsrEncoderConfig {
+  int32_t d_model;
+  int32_t n_heads;
+  int32_t linear_units;
+  int32_t num_blocks;
+  int32_t cnn_kernel;
+} AvsrEncoderConfig;
+
+/* One EncoderLayer's parameters in the reference's own layout and naming
+ * (espnet/nets/pytorch_backend/encoder/conformer_encoder.py:61-94; the 40 state-dict keys of SURVEY.md 8a,
+ * minus num_batches_tracked).  Linear weights are (out, in); conv weights keep their trailing 1-dims. */
+typedef struct AvsrLayerParams {
+  /* feed_forward_macaron.{w_1,w_2} + norm_ff_macaron   (positionwise_feed_forward.py:24-30) */
+  const float *ffm_w1, *ffm_b1, *ffm_w2, *ffm_b2, *norm_ffm_w, *norm_ffm_b;
+  /* self_attn.*  + norm_mha                            (transformer/attention.py:31-34,118-129) */
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *out_w, *out_b, *pos_w, *pos_bias_u, *pos_bias_v;
+  const float *norm_mha_w, *norm_mha_b;
+  /* conv_module.* + norm_conv                          (conformer_encoder.py:20-28) */
+  const float *pw1_w, *pw1_b, *dw_w, *dw_b, *bn_w, *bn_b, *bn_mean, *bn_var, *pw2_w, *pw2_b;
+  const float *norm_conv_w, *norm_conv_b;
+  /* feed_forward.{w_1,w_2} + norm_ff */
+  const float *ff_w1, *ff_b1, *ff_w2, *ff_b2, *norm_ff_w, *norm_ff_b;
+  /* norm_final */
+  const float *norm_final_w, *norm_final_b;
+} AvsrLayerParams;
+
+/* ---- library / error -------------------------------------------------------------------------- */
+int avsr_abi_version(void);
+const char *avsr_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t avsr_launch_count(void);
+
+/* ---- weight preparation ------------------------------------------------------------------------
+ * Replaces nothing in the reference (it uses nn.Parameters in place); it is the one-off layout step
+ * of this implementation: QK weights concatenated, pointwise_cov1 rows interleaved so a GEMM tile
+ * holds GLU value+gate pairs, depthwise taps transposed to (K, C), BatchNorm running statistics
+ * (conformer_encoder.py:26, eval mode) folded into scale/shift, linear_pos of all layers stacked, and --
+ * for AVSR_PREC_TF32 -- GEMM weights rounded to TF32 (round-to-nearest) so the tensor core's operand
+ * truncation is exact.  `layers` is a HOST array of num_blocks structs holding DEVICE pointers.
+ * Must be re-run after the parameters change. */
+size_t avsr_prepared_bytes(const AvsrEncoderConfig *cfg);
+int avsr_prepare_weights(const AvsrEncoderConfig *cfg, const AvsrLayerParams *layers,
+                         const float *after_norm_w, const float *after_norm_b,
+                         void *prepared, size_t prepared_bytes, int precision, void *stream);
+
+/* ---- whole-encoder forward ---------------------------------------------------------------------
+ * ConformerEncoder.forward(xs, masks) in eval mode (conformer_encoder.py:264-282): embed (x*sqrt(d),
+ * rel-pos sinusoid table, transformer/embedding.py:171-184) -> num_blocks x EncoderLayer.forward
+ * (conformer_encoder.py:96-170) -> after_norm.
+ *   xs      (B, T, d_model) fp32      lengths (B) int32 DEVICE array or NULL
+ *   out     (B, T, d_model) fp32
+ * `lengths` is the prefix form of the reference's masks (B,1,T) = make_non_pad_mask(lengths)
+ * (nets_utils.py:183); NULL == masks None == every frame valid.  As in the reference only attention
+ * KEYS are masked: padded frames are computed as data everywhere else. */
+size_t avsr_workspace_bytes(const AvsrEncoderConfig *cfg, int B, int T);
+int avsr_encoder_forward(const AvsrEncoderConfig *cfg, const void *prepared, const float *xs,
+                         const int32_t *lengths, int B, int T, float *out, void *workspace,
+                         size_t workspace_bytes, int precision, void *stream);
+
+/* Same computation replayed from a CUDA graph captured once per (B, T, buffers): removes the ~190
+ * per-forward launches' host cost.  The plan is HOST state only (tensor maps + graph); it borrows
+ * `prepared` and `workspace`, which must outlive it and must not be used by another plan concurrently. */
+typedef struct AvsrPlan AvsrPlan;
+int avsr_plan_create(const AvsrEncoderConfig *cfg, const void *prepared, int B, int T, void *workspace,
+                     size_t workspace_bytes, int precision, void *stream, AvsrPlan **plan);
+int avsr_plan_forward(AvsrPlan *plan, const float *xs, const int32_t *lengths, float *out, void *stream);
+void avsr_plan_destroy(AvsrPlan *plan);
+
+/* layer-0 residual-stage taps for parity debugging: after avsr_encoder_forward with taps enabled the
+ * 5 stage outputs of layer 0 (conformer_encoder.py:110-162) are copied to `taps` (5, B*T, d_model). */
+int avsr_encoder_forward_taps(const AvsrEncoderConfig *cfg, const void *prepared, const float *xs,
+                              const int32_t *lengths, int B, int T, float *out, float *taps,
+                              void *workspace, size_t workspace_bytes, int precision, void *stream);
+
+/* ---- per-op entry points (unit parity) --------------------------------------------------------- */
+
+/* LayerNorm(d, eps=1e-12) over the last dim (transformer/layer_norm.py:12-33).  rows x d. */
+int avsr_layernorm(const float *x, const float *gamma, const float *beta, float *y, int rows, int d,
+                   void *stream);
+
+/* torch.nn.Linear: y = x W^T + b, optionally ReLU (positionwise_feed_forward.py:30) and/or
+ * y = resid + alpha*y (conformer_encoder.py:115,140,150,158).  x (rows,k); w (n,k); bias (n) or NULL;
+ * resid (rows,n) or NULL (may alias y). */
+int avsr_linear(const float *x, const float *w, const float *bias, const float *resid, float alpha,
+                int relu, float *y, int rows, int n, int k, int precision, void *stream);
+
+/* RelPositionMultiHeadedAttention core (transformer/attention.py:174-189 + :59-82), d_k = 64:
+ *   scores[b,h,i,j] = ((q_i+u_h).k_j + (q_i+v_h).p_h[rel=i-j]) / 8, key mask j >= lengths[b],
+ *   softmax over j (fully masked row -> zeros), ctx = attn @ v.
+ *   q,k,v (B,T,H*64) already projected (biases added); p (2T-1, H*64) = linear_pos(pos_emb), row m <-> rel=T-1-m;
+ *   u,v_bias (H,64); ctx (B,T,H*64).  workspace >= avsr_attention_workspace_bytes(B,T,H). */
+size_t avsr_attention_workspace_bytes(int B, int T, int H);
+int avsr_relpos_attention(const float *q, const float *k, const float *v, const float *p,
+                          const float *pos_bias_u, const float *pos_bias_v, const int32_t *lengths,
+                          float *ctx, int B, int T, int H, void *workspace, size_t workspace_bytes,
+                          int precision, void *stream);
+
+/* Depthwise Conv1d(C, C, K, padding=(K-1)/2, groups=C) + BatchNorm1d(eval) + SiLU over (B,T,C)
+ * (conformer_encoder.py:33 with :25-28); zero 'same' padding per utterance row, no length mask.
+ *   w (C,1,K) reference layout; everything else (C).  workspace >= (K+2)*C floats (folded taps/scale/shift). */
+int avsr_dwconv_bn_silu(const float *x, const float *w, const float *b, const float *bn_w,
+                        const float *bn_b, const float *bn_mean, const float *bn_var, float *y, int B,
+                        int T, int C, int K, void *workspace, size_t workspace_bytes, void *stream);
+
+/* pointwise_cov1 + GLU (conformer_encoder.py:32): y = glu(x W^T + b) over channels, W (2C, C[,1]), b (2C),
+ * x (rows, C) -> y (rows, C).  workspace >= (2C*C + 2C) floats (interleaved copy of W, b). */
+int avsr_pointwise_glu(const float *x, const float *w, const float *b, float *y, int rows, int C,
+                       void *workspace, size_t workspace_bytes, int precision, void *stream);
+
+/* pos_emb table of RelPositionalEncoding (transformer/embedding.py:139-184): (2T-1, d) fp32, row m = sinusoid(T-1-m). */
+int avsr_rel_sinusoid_table(float *pe, int T, int d, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSR_B200_H_ */

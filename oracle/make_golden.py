@@ -103,6 +103,12 @@ def main():
         print(case["name"], "out", tuple(out64.shape), "f32-vs-f64 max-abs",
               (out32.double() - out64).abs().max().item(), os.path.getsize(path) // 1024, "KiB")
 
+    # the state-dict contract: key -> shape of the reference's default-config encoder
+    enc = ConformerEncoder()
+    with open(os.path.join(ROOT, "tests", "golden", "encoder_state_keys.txt"), "w") as f:
+        for k, v in enc.state_dict().items():
+            f.write(f"{k} {' '.join(str(d) for d in v.shape)}\n")
+
     # known-answer table from the reference docstring (nets_utils.py:82-90): lengths [5,3,2]
     m = make_pad_mask([5, 3, 2])
     np.savez(os.path.join(ROOT, "tests", "golden", "pad_mask_532.npz"),

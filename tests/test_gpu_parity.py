@@ -1,0 +1,278 @@
+"""GPU parity tests proper: every call goes through the C ABI (ctypes) of libavsr_b200.so and is compared with
+the CPU oracle / the committed golden vectors of the reference.
+
+Tolerances (max-abs on outputs of rms ~1 unless noted):
+  fp32 path  (CUDA-core FMA):       2e-4 whole encoder, 2e-5 single ops -- fp32 summation-order noise only
+  tf32 path  (tcgen05 kind::tf32):  2e-2 max-abs / 3e-3 rms whole 12-layer encoder; operands rounded to TF32
+                                    (10-bit mantissa, RN), fp32 accumulate -- the same class of arithmetic
+                                    PyTorch's own `allow_tf32` GPU path uses for the reference.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import err_stats, load_case
+from oracle import conformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRECS = ["fp32", "tf32"]
+TOL_ENC = {"fp32": (2e-4, 2e-5), "tf32": (2e-2, 3e-3)}       # (max-abs, rms) vs the fp64 reference
+TOL_OP = {"fp32": 2e-5, "tf32": 4e-3}                         # relative to output scale
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "run with gpurun"
+    import __graft_entry__ as g
+    g.build()
+    return torch.device("cuda:0")
+
+
+def _encoder(case, dev, prec):
+    from auto_avsr_b200 import ConformerEncoder
+    cfg = case["cfg"]
+    enc = ConformerEncoder(attention_dim=cfg["d_model"], attention_heads=cfg["n_heads"],
+                           linear_units=cfg["linear_units"], num_blocks=cfg["num_blocks"],
+                           cnn_module_kernel=cfg["cnn_kernel"])
+    enc.load_state_dict(case["sd"], strict=True)
+    enc = enc.to(dev).eval()
+    enc.precision = prec
+    return enc
+
+
+def _mask(case, dev):
+    return O.non_pad_mask(case["lengths"]).unsqueeze(1).to(dev) if case["masked"] else None
+
+
+# ------------------------------------------------------------------------------------------ unit ops
+def test_layernorm(dev):
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for rows, d in [(1, 768), (37, 768), (1600, 768), (5, 128), (9, 1024), (3, 4)]:
+        x = torch.randn(rows, d, generator=g) * 3 + 0.5
+        w, b = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g) * 0.1
+        y = ops.layernorm(x.to(dev), w.to(dev), b.to(dev)).cpu()
+        ref = O.layer_norm(x.double(), w.double(), b.double())
+        assert err_stats(y, ref)[0] < 5e-6 * max(1.0, ref.abs().max().item()), (rows, d)
+    # constant rows: variance 0 -> eps 1e-12 keeps it finite and equal to beta
+    x = torch.full((2, 768), 3.25)
+    y = ops.layernorm(x.to(dev), torch.ones(768, device=dev), torch.full((768,), 0.5, device=dev)).cpu()
+    assert torch.allclose(y, torch.full_like(y, 0.5))
+
+
+def test_sinusoid_table(dev):
+    from auto_avsr_b200 import ops
+    for T, d in [(1, 768), (7, 16), (100, 768), (400, 768)]:
+        pe = ops.rel_sinusoid_table(T, d, dev).cpu()
+        ref = O.rel_sinusoid_table(T, d, torch.float32)
+        assert pe.shape == ref.shape
+        assert err_stats(pe, ref)[0] < 2e-6 * max(1, T / 100), (T, d)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_linear(dev, prec):
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    for rows, n, k in [(200, 768, 768), (129, 3072, 768), (77, 768, 3072), (1, 128, 256), (300, 256, 128),
+                       (1600, 768, 768)]:
+        x = torch.randn(rows, k, generator=g)
+        w = (torch.rand(n, k, generator=g) * 2 - 1) / math.sqrt(k)
+        b = torch.randn(n, generator=g) * 0.1
+        r = torch.randn(rows, n, generator=g)
+        ref = x.double() @ w.double().T + b.double()
+        scale = ref.abs().max().item()
+        y = ops.linear(x.to(dev), w.to(dev), b.to(dev), precision=prec).cpu()
+        assert err_stats(y, ref)[0] < TOL_OP[prec] * scale, (rows, n, k)
+        y = ops.linear(x.to(dev), w.to(dev), b.to(dev), relu=True, precision=prec).cpu()
+        assert err_stats(y, ref.clamp_min(0))[0] < TOL_OP[prec] * scale
+        y = ops.linear(x.to(dev), w.to(dev), None, residual=r.to(dev), alpha=0.5, precision=prec).cpu()
+        assert err_stats(y, r.double() + 0.5 * (ref - b.double()))[0] < TOL_OP[prec] * scale
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_pointwise_glu(dev, prec):
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for rows, C in [(150, 768), (33, 128)]:
+        x = torch.randn(rows, C, generator=g)
+        w = (torch.rand(2 * C, C, 1, generator=g) * 2 - 1) / math.sqrt(C)
+        b = torch.randn(2 * C, generator=g) * 0.1
+        y = ops.pointwise_glu(x.to(dev), w.to(dev), b.to(dev), prec).cpu()
+        full = x.double() @ w.squeeze(-1).double().T + b.double()
+        ref = full[:, :C] * torch.sigmoid(full[:, C:])
+        assert err_stats(y, ref)[0] < TOL_OP[prec] * max(1.0, ref.abs().max().item()), (rows, C)
+
+
+def test_dwconv_bn_silu(dev):
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for B, T, C, K in [(3, 37, 128, 31), (1, 5, 768, 31), (2, 100, 768, 31), (1, 23, 128, 7), (2, 64, 64, 1)]:
+        x = torch.randn(B, T, C, generator=g)
+        w = torch.randn(C, 1, K, generator=g) / math.sqrt(K)
+        b, bw, bb = (torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5,
+                     torch.randn(C, generator=g) * 0.1)
+        mean, var = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+        y = ops.dwconv_bn_silu(*[t.to(dev) for t in (x, w, b, bw, bb, mean, var)]).cpu()
+        conv = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(K - 1) // 2,
+                                          groups=C)
+        h = (conv - mean.double()[:, None]) / torch.sqrt(var.double()[:, None] + 1e-5) * bw.double()[:, None] \
+            + bb.double()[:, None]
+        ref = (h * torch.sigmoid(h)).transpose(1, 2)
+        assert err_stats(y, ref)[0] < 1e-5 * max(1.0, ref.abs().max().item()), (B, T, C, K)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_relpos_attention(dev, prec):
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for B, T, H, lengths in [(3, 37, 2, [37, 29, 18]), (1, 100, 12, None), (2, 130, 3, [130, 1]),
+                             (2, 9, 2, [0, 9]), (1, 1, 2, None), (2, 257, 2, [257, 200])]:
+        D = H * 64
+        q, k, v = (torch.randn(B, T, D, generator=g) for _ in range(3))
+        p = torch.randn(2 * T - 1, D, generator=g)
+        u, vb = torch.randn(H, 64, generator=g) * 0.3, torch.randn(H, 64, generator=g) * 0.3
+        ln = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
+        ctx = ops.relpos_attention(q.to(dev), k.to(dev), v.to(dev), p.to(dev), u.to(dev), vb.to(dev), ln, H,
+                                   precision=prec).cpu()
+
+        def heads(t):
+            return t.double().view(B, T, H, 64).transpose(1, 2)
+        scores = O.rel_attention_scores(heads(q), heads(k), p.double().view(2 * T - 1, H, 64).transpose(0, 1),
+                                        u.double(), vb.double())
+        if lengths is not None:
+            pad = torch.arange(T)[None, :] >= torch.tensor(lengths)[:, None]
+            scores = scores.masked_fill(pad[:, None, None, :], float("-inf"))
+        attn = torch.softmax(scores, dim=-1)
+        attn = torch.where(torch.isnan(attn), torch.zeros_like(attn), attn)       # fully masked rows -> 0
+        ref = (attn @ heads(v)).transpose(1, 2).reshape(B, T, D)
+        tol = 2e-5 if prec == "fp32" else 2e-2     # scores of randn q,k have sd ~8: tf32 input rounding shows
+        assert err_stats(ctx, ref)[0] < tol * max(1.0, ref.abs().max().item()), (B, T, H, lengths)
+
+
+# ------------------------------------------------------------------------------------------ whole encoder
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", ["tiny_ragged", "tiny_k7_nomask", "full2_ragged", "full12_s1", "full12_ragged"])
+def test_encoder_matches_reference_golden(dev, name, prec):
+    c = load_case(name)
+    enc = _encoder(c, dev, prec)
+    ref = torch.from_numpy(c["z"]["out_f64"]).double()
+    outs = {}
+    for graph in (False, True):
+        enc.use_graph = graph
+        out, m = enc(c["xs"].to(dev), _mask(c, dev))
+        outs[graph] = out.cpu()
+        mx, rms = err_stats(outs[graph], ref)
+        assert mx < TOL_ENC[prec][0] and rms < TOL_ENC[prec][1], (name, prec, graph, mx, rms)
+        assert (m is None) == (not c["masked"])
+    assert torch.equal(outs[False], outs[True]), "CUDA-graph replay must be bit-identical to direct launches"
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", ["tiny_ragged", "full2_ragged"])
+def test_layer0_stage_taps(dev, name, prec):
+    c = load_case(name)
+    enc = _encoder(c, dev, prec)
+    B, T, D = c["xs"].shape
+    taps = torch.empty(5, B * T, D, device=dev)
+    enc(c["xs"].to(dev), _mask(c, dev), taps=taps)
+    for i in range(5):
+        g = torch.from_numpy(c["z"][f"stage{i}"]).double().reshape(B * T, D)
+        mx, rms = err_stats(taps[i].cpu(), g)
+        scale = g.abs().max().item()
+        tol = 2e-5 if prec == "fp32" else 3e-3
+        assert mx < tol * scale, (name, prec, i, mx, scale)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_per_module_layer_forward(dev, prec):
+    """EncoderLayer / sub-module forwards (per-op C-ABI entry points) agree with the fused whole-encoder call."""
+    c = load_case("tiny_ragged")
+    enc = _encoder(c, dev, prec)
+    for m in enc.modules():
+        if hasattr(m, "precision"):
+            m.precision = prec
+    xs, mask = c["xs"].to(dev), _mask(c, dev)
+    x, pos = enc.embed(xs)
+    (x, _), _ = enc.encoders((x, pos), mask)
+    y = enc.after_norm(x).cpu()
+    ref = torch.from_numpy(c["z"]["out_f64"])
+    mx, rms = err_stats(y, ref)
+    assert mx < TOL_ENC[prec][0] and rms < TOL_ENC[prec][1], (mx, rms)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_size_s2_against_oracle(dev, prec):
+    """BASELINE.json configs[1]: 12 layers, d=768, max-frames 1600 as [400]*4 -- compared with the fp32 CPU oracle
+    (itself pinned to the reference, tests/test_oracle_golden.py) and checked for batch-independence."""
+    from auto_avsr_b200.synthetic import SHAPES, encoder_input, encoder_state_dict
+    lengths = SHAPES["S2"]
+    sd = encoder_state_dict(0)
+    xs = encoder_input(lengths, 768, 1234)
+    case = dict(cfg=dict(d_model=768, n_heads=12, linear_units=3072, num_blocks=12, cnn_kernel=31), sd=sd)
+    enc = _encoder(case, dev, prec)
+    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+    out = enc(xs.to(dev), mask)[0].cpu()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.encoder_forward(sd, xs.float(), lengths, 12)
+    mx, rms = err_stats(out, ref)
+    assert mx < TOL_ENC[prec][0] and rms < TOL_ENC[prec][1], (prec, mx, rms)
+    assert torch.isfinite(out).all()
+    # utterances do not interact (no padding here): running utterance 2 alone gives the same rows
+    alone = enc(xs[2:3].to(dev), None)[0].cpu()
+    mx2, _ = err_stats(alone[0], out[2])
+    assert mx2 < (1e-5 if prec == "fp32" else 5e-3), mx2
+    # batch permutation permutes the output
+    perm = [3, 1, 0, 2]
+    outp = enc(xs[perm].to(dev), mask)[0].cpu()
+    assert err_stats(outp, out[perm])[0] < (1e-5 if prec == "fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_edge_shapes(dev, prec):
+    from auto_avsr_b200 import ConformerEncoder
+    from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict
+    sd = encoder_state_dict(5, num_blocks=1)
+    enc = ConformerEncoder(num_blocks=1)
+    enc.load_state_dict(sd)
+    enc = enc.to(dev).eval()
+    enc.precision = prec
+    # empty batch / zero frames
+    assert enc(torch.zeros(0, 10, 768, device=dev), None)[0].shape == (0, 10, 768)
+    assert enc(torch.zeros(2, 0, 768, device=dev), None)[0].shape == (2, 0, 768)
+    tol = TOL_ENC[prec][0]
+    for lengths, masked in [([1], False), ([3, 2], True), ([130, 127, 5], True), ([17, 0], True), ([33], False)]:
+        xs = encoder_input(lengths, 768, 99)
+        if max(lengths) == 17:            # zero-length utterance: keep T = 17
+            xs = encoder_input([17, 17], 768, 99)
+        mask = O.non_pad_mask(lengths, xs.size(1)).unsqueeze(1).to(dev) if masked else None
+        out = enc(xs.to(dev), mask)[0].cpu()
+        ref = O.encoder_forward(sd, xs.double(), lengths if masked else None, 12)
+        mx, _ = err_stats(out, ref)
+        assert mx < tol, (lengths, masked, mx)
+
+
+def test_weight_refresh_on_parameter_update(dev):
+    from auto_avsr_b200 import ConformerEncoder
+    from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict
+    enc = ConformerEncoder(num_blocks=1)
+    enc.load_state_dict(encoder_state_dict(5, num_blocks=1))
+    enc = enc.to(dev).eval()
+    enc.precision = "fp32"
+    xs = encoder_input([20], 768, 1).to(dev)
+    a = enc(xs, None)[0].clone()
+    sd2 = encoder_state_dict(6, num_blocks=1)
+    enc.load_state_dict(sd2)                       # in-place copy_ bumps tensor versions -> weights re-prepared
+    b = enc(xs, None)[0]
+    ref = O.encoder_forward(sd2, xs.cpu().double(), None, 12)
+    assert not torch.allclose(a, b)
+    assert err_stats(b.cpu(), ref)[0] < 2e-4
+
+
+def test_launch_counter_counts_kernels(dev):
+    from auto_avsr_b200 import _cabi, ops
+    before = _cabi.launch_count()
+    ops.layernorm(torch.randn(4, 768, device=dev), torch.ones(768, device=dev), torch.zeros(768, device=dev))
+    assert _cabi.launch_count() == before + 1
