@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: Conformer encoder forward, frames/sec at max-frames=1600 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision tf32|fp32]
+
+A step = one ConformerEncoder.forward (embed + 12 layers + after_norm, eval) over one synthetic max-frames=1600
+bucket per GPU (workload S2 = 4 utterances x 400 frames, d=768, BASELINE.json configs[1]); weak scaling: every
+rank gets its own bucket, no collective on the data path; value = all ranks' valid frames / max-over-ranks time.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference (oracle/) on the
+host cores instead (the reference itself is Python and lives outside the repo, so it cannot travel to the GPU
+box; the oracle is pinned to it by tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from auto_avsr_b200.synthetic import SHAPES, encoder_input, encoder_state_dict  # noqa: E402
+
+WORKLOAD = "S2"
+CFG = dict(d_model=768, n_heads=12, linear_units=3072, num_blocks=12, cnn_kernel=31)
+METRIC = "conformer_encoder_frames_per_sec_max_frames_1600"
+
+
+def algorithmic_flops(lengths, warm_pos_cache=False):
+    """326,154,240*sum(L) + 55,296*sum(L^2) + 14,155,776*(2*Tmax-1) (valid frames only)."""
+    s1 = sum(lengths)
+    s2 = sum(v * v for v in lengths)
+    pos = 0 if warm_pos_cache else 14_155_776 * (2 * max(lengths) - 1)
+    return 326_154_240 * s1 + 55_296 * s2 + pos
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained"),
+                    hbm_gbs=p["hbm_gbs"], source="measured")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if mx and v > 0.3 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_time(lengths, repeats, threads):
+    """Best-of-`repeats` wall time of one forward of the CPU oracle (fp32, eval) on `threads` host threads."""
+    from oracle import conformer_oracle as O
+    torch.set_num_threads(threads)
+    sd = encoder_state_dict(0, **CFG)
+    xs = encoder_input(lengths, CFG["d_model"], 1234)
+    with torch.no_grad():
+        O.encoder_forward(sd, xs, lengths, CFG["n_heads"])          # warm-up
+        best = float("inf")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    lengths = list(SHAPES[WORKLOAD])
+    threads = os.cpu_count() or 1
+    from oracle import conformer_oracle as O
+    torch.set_num_threads(threads)
+    sd = encoder_state_dict(0, **CFG)
+    xs = encoder_input(lengths, CFG["d_model"], 1234)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
+        dt = time.perf_counter() - t0
+    fps = sum(lengths) * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD} lengths={lengths} d=768 L=12 (BASELINE.json configs[1])",
+                   "impl_note": "CPU restatement of the reference encoder (oracle/, pinned to reference golden "
+                                "vectors); rank 0 only, host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full forwards of workload {WORKLOAD} (1600 frames each)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_roofline(dev, peaks, precision):
+    """Dominant kernel = the tcgen05 TF32 GEMM (96% of the forward's FLOPs).  Times its largest instance, the FFN
+    w_1 projection (1600 x 3072 x 768, 24 launches per forward), over 24 distinct weight matrices back to back
+    with CUDA events on the launch stream; achieved = algorithmic 2*M*N*K per launch / mean launch duration."""
+    from auto_avsr_b200 import ops
+    M, N, K = 1600, 3072, 768
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(M, K, generator=g).to(dev)
+    ws = [(torch.rand(N, K, generator=g) - 0.5).to(dev) for _ in range(24)]
+    b = torch.zeros(N, device=dev)
+    for w in ws[:3]:
+        ops.linear(x, w, b, relu=True, precision=precision)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    e0.record()
+    for _ in range(reps):
+        for w in ws:
+            ops.linear(x, w, b, relu=True, precision=precision)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * len(ws))
+    flops = 2.0 * M * N * K
+    achieved = flops / per_launch_s / 1e12
+    peak = peaks["bf16_tflops"]
+    prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    traffic = None
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_LINEAR,128> FFN w_1 1600x3072x768 (tcgen05 kind::tf32)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks['source']}); kind::tf32 nominal peak is 0.5x bf16",
+            "frac_of_tf32_nominal": achieved / (0.5 * peak), "us_per_launch": per_launch_s * 1e6,
+            "algorithmic_flops_per_launch": flops, "traffic": traffic}
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the encoder path has no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from auto_avsr_b200 import ConformerEncoder, _cabi
+    from oracle import conformer_oracle as O   # only non_pad_mask + the cpu_baseline leg
+
+    lengths = list(SHAPES[WORKLOAD])
+    B, T, D = len(lengths), max(lengths), CFG["d_model"]
+    enc = ConformerEncoder(attention_dim=D, attention_heads=CFG["n_heads"], linear_units=CFG["linear_units"],
+                           num_blocks=CFG["num_blocks"], cnn_module_kernel=CFG["cnn_kernel"])
+    enc.load_state_dict(encoder_state_dict(0, **CFG), strict=True)
+    enc = enc.to(dev).eval()
+    enc.precision = args.precision
+    enc.assume_frozen = True
+    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+    nbuf = 4     # rotating inputs; the 682 MB of weights streamed every step already exceed the 126 MB L2
+    host_in = [encoder_input(lengths, D, 1234 + rank * 100 + i).pin_memory() for i in range(nbuf)]
+    dev_in = [h.to(dev) for h in host_in]
+    host_out = torch.empty(B, T, D).pin_memory()
+    host_len = torch.tensor(lengths, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            enc(dev_in[i % nbuf], mask)
+        barrier()
+        # ---- device-resident timing: CUDA events on the launch stream
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = _cabi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            enc(dev_in[i % nbuf], mask)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _cabi.launch_count() - l0
+        clocks = sampler.stop()
+        # ---- end to end through the public module API: pinned H2D of the inputs, forward, D2H of the features
+        for i in range(2):
+            x = host_in[i % nbuf].to(dev, non_blocking=True)
+            out, _ = enc(x, O.non_pad_mask(lengths).unsqueeze(1).to(dev))
+            host_out.copy_(out, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            x = host_in[i % nbuf].to(dev, non_blocking=True)
+            ln = host_len.to(dev, non_blocking=True)
+            m = (torch.arange(T, device=dev)[None, :] < ln[:, None]).unsqueeze(1)   # make_non_pad_mask on device
+            out, _ = enc(x, m)
+            host_out.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = t_ms.tolist()
+    frames = sum(lengths) * args.steps * world
+    value = frames / (ms_max * 1e-3)
+    e2e_value = frames / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: lengths={lengths} (max-frames=1600 per GPU), d=768 H=12 ff=3072 L=12 k=31, "
+                                   "eval forward, BASELINE.json configs[1]",
+                       "global_frames_per_step": sum(lengths) * world, "parallelism": f"dp{world} (one bucket per GPU, "
+                                                                                       "no data-path collective)",
+                       "l2": "682 MB of weights streamed per step > 126 MB L2; 4 rotating input buffers",
+                       "pos_cache": "cold: linear_pos(pos_emb) recomputed every step", "precision": args.precision},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 4 + B * 4,
+                    "d2h_bytes_per_step": B * T * D * 4, "ms_per_step": e2e_ms_max / args.steps,
+                    "api": "auto_avsr_b200.ConformerEncoder.forward(xs, masks) -> avsr_plan_forward (C ABI)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "forward_model": {"algorithmic_gflop_per_step": algorithmic_flops(lengths) / 1e9,
+                              "achieved_tflops": algorithmic_flops(lengths) / (ms_max / args.steps * 1e-3) / 1e12,
+                              "frac_of_bf16_peak": algorithmic_flops(lengths) / (ms_max / args.steps * 1e-3) / 1e12
+                              / peaks["bf16_tflops"]},
+        }
+        if args.precision == "tf32":
+            line["roofline"] = kernel_roofline(dev, peaks, args.precision)
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            best = cpu_oracle_time(lengths, repeats=3, threads=threads)
+            line["cpu_baseline"] = {"value": sum(lengths) / best, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"best of 3 full forwards of workload {WORKLOAD} (1600 frames), fp32, "
+                                              "after 1 warm-up"}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AVSR_B200_PRECISION", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20          # ~1 s per CPU forward: keep the arm within a few minutes
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

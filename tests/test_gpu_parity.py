@@ -69,7 +69,8 @@ def test_sinusoid_table(dev):
         pe = ops.rel_sinusoid_table(T, d, dev).cpu()
         ref = O.rel_sinusoid_table(T, d, torch.float32)
         assert pe.shape == ref.shape
-        assert err_stats(pe, ref)[0] < 2e-6 * max(1, T / 100), (T, d)
+        # a 1-ulp difference in the fp32 frequency exp() moves the fp32 argument rel*w by up to T * 6e-8
+        assert err_stats(pe, ref)[0] < 1e-6 + 1.5e-7 * T, (T, d)
 
 
 @pytest.mark.parametrize("prec", PRECS)
