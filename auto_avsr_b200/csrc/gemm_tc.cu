@@ -39,7 +39,7 @@ static EncodeTiledFn encode_tiled_fn() {
 int make_tmap_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return AVSR_E_CUDA; }
-  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0 && cols >= 32 && box_rows <= 256,
+  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0 && box_rows <= 256,
                "tensor map: base/stride must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * sizeof(float)};

@@ -56,11 +56,9 @@ def rel_sinusoid_table(T: int, d_model: int, dtype=torch.float32) -> Tensor:
 
 
 def layer_norm(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
-    """LayerNorm over the last dim, eps 1e-12 (transformer/layer_norm.py:12-33)."""
-    mu = x.mean(dim=-1, keepdim=True)
-    xc = x - mu
-    var = (xc * xc).mean(dim=-1, keepdim=True)
-    return xc * torch.rsqrt(var + LN_EPS) * w + b
+    """LayerNorm over the last dim, eps 1e-12 (transformer/layer_norm.py:12-33):
+    (x - mean) / sqrt(biased_var + eps) * w + b."""
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, LN_EPS)
 
 
 def feed_forward(x: Tensor, sd: Dict[str, Tensor], pfx: str) -> Tensor:
@@ -132,14 +130,11 @@ def conv_module(x: Tensor, sd: Dict[str, Tensor], pfx: str) -> Tensor:
     w1 = sd[pfx + "pointwise_cov1.weight"].squeeze(-1)                          # (2D, D)
     y = x @ w1.T + sd[pfx + "pointwise_cov1.bias"]
     g = y[..., :D] * torch.sigmoid(y[..., D:])                                  # GLU over channels
-    wd = sd[pfx + "depthwise_conv.weight"].squeeze(1)                           # (D, K)
-    K = wd.shape[1]
-    half = (K - 1) // 2
-    gp = torch.nn.functional.pad(g, (0, 0, half, half))                         # pad time
-    acc = torch.zeros_like(g)
-    for t in range(K):                                                          # cross-correlation
-        acc = acc + gp[:, t:t + T, :] * wd[:, t]
-    acc = acc + sd[pfx + "depthwise_conv.bias"]
+    wd = sd[pfx + "depthwise_conv.weight"]                                      # (D, 1, K)
+    half = (wd.shape[-1] - 1) // 2
+    # depthwise cross-correlation along time, zero padding `half` frames each side of every utterance row
+    acc = torch.nn.functional.conv1d(g.transpose(1, 2), wd, sd[pfx + "depthwise_conv.bias"], padding=half,
+                                     groups=D).transpose(1, 2)
     scale = sd[pfx + "norm.weight"] * torch.rsqrt(sd[pfx + "norm.running_var"] + BN_EPS)
     h = (acc - sd[pfx + "norm.running_mean"]) * scale + sd[pfx + "norm.bias"]
     h = h * torch.sigmoid(h)                                                    # SiLU
