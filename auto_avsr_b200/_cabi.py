@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libavsr_b200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
-PREC_FP32, PREC_TF32 = 0, 1
-ABI_VERSION = 1
+PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
+ABI_VERSION = 2
 
 
 class AvsrError(RuntimeError):
@@ -68,10 +68,13 @@ SIGNATURES = {
     "avsr_plan_forward": (_I, [_P, _P, _P, _P, _P]),
     "avsr_plan_destroy": (None, [_P]),
     "avsr_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
-    "avsr_linear": (_I, [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _P]),
+    "avsr_linear_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "avsr_linear": (_I, [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "avsr_linear_operands": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "avsr_attention_workspace_bytes": (_Z, [_I, _I, _I]),
     "avsr_relpos_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "avsr_dwconv_bn_silu": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "avsr_pointwise_glu_workspace_bytes": (_Z, [_I, _I]),
     "avsr_pointwise_glu": (_I, [_P, _P, _P, _P, _I, _I, _P, _Z, _I, _P]),
     "avsr_rel_sinusoid_table": (_I, [_P, _I, _I, _P]),
 }

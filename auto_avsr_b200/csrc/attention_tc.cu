@@ -251,11 +251,11 @@ int attention_tc(const float* qu, const float* qv, const float* kk, const float*
   if (B <= 0 || T <= 0) return AVSR_OK;
   CUtensorMap tmQu, tmQv, tmK, tmV, tmP;
   const uint64_t rows = (uint64_t)B * H * T;
-  AVSR_TRY(make_tmap_2d(&tmQu, qu, rows, 64, 64, AT_BQ));
-  AVSR_TRY(make_tmap_2d(&tmQv, qv, rows, 64, 64, AT_BQ));
-  AVSR_TRY(make_tmap_2d(&tmK, kk, rows, 64, 64, AT_BKV));
-  AVSR_TRY(make_tmap_2d(&tmV, vt, (uint64_t)B * H * 64, (uint64_t)Tp, (uint64_t)Tp, 64));
-  AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AT_BAND));
+  AVSR_TRY(make_tmap_2d(&tmQu, qu, rows, 64, 64, AT_BQ, 4));
+  AVSR_TRY(make_tmap_2d(&tmQv, qv, rows, 64, 64, AT_BQ, 4));
+  AVSR_TRY(make_tmap_2d(&tmK, kk, rows, 64, 64, AT_BKV, 4));
+  AVSR_TRY(make_tmap_2d(&tmV, vt, (uint64_t)B * H * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 4));
+  AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AT_BAND, 4));
   static bool attr_done = false;
   if (!attr_done) {
     AVSR_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));

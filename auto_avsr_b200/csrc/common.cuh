@@ -1,5 +1,6 @@
 // Shared internals of libavsr_b200: error plumbing, launch accounting, the GEMM epilogue family.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,6 +70,48 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- tensor-core operand storage
+// How a tensor that feeds a tensor-core contraction is stored:
+//   OP_F32  : plain fp32 (CUDA-core reference path)
+//   OP_TF32 : fp32 container, value rounded to TF32 (10-bit mantissa) -> tcgen05 kind::tf32
+//   OP_F16  : IEEE half (same 10-bit mantissa as TF32, 5-bit exponent, saturating) -> tcgen05 kind::f16;
+//             half the bytes through L2/shared memory and twice the MMA rate of kind::tf32
+enum OperandKind : int { OP_F32 = 0, OP_TF32 = 1, OP_F16 = 2 };
+
+__device__ __forceinline__ __half to_half_sat(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return __ushort_as_half(r);
+}
+// store 4 consecutive operand values (dst 16-byte aligned for float, 8-byte aligned for half)
+template <typename TOp>
+__device__ __forceinline__ void store_op4(TOp* dst, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_op4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(a), round_tf32(b), round_tf32(c), round_tf32(d));
+}
+template <>
+__device__ __forceinline__ void store_op4<__half>(__half* dst, float a, float b, float c, float d) {
+  __half2 lo = __halves2half2(to_half_sat(a), to_half_sat(b));
+  __half2 hi = __halves2half2(to_half_sat(c), to_half_sat(d));
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = v;
+}
+template <typename TOp>
+__device__ __forceinline__ void store_op1(TOp* dst, float a);
+template <>
+__device__ __forceinline__ void store_op1<float>(float* dst, float a) { *dst = round_tf32(a); }
+template <>
+__device__ __forceinline__ void store_op1<__half>(__half* dst, float a) { *dst = to_half_sat(a); }
+// runtime-kind store used by the elementwise kernels (kind is warp-uniform)
+__device__ __forceinline__ void store_kind4(void* base, long idx, int kind, float a, float b, float c, float d) {
+  if (kind == OP_F16) store_op4<__half>(reinterpret_cast<__half*>(base) + idx, a, b, c, d);
+  else if (kind == OP_TF32) store_op4<float>(reinterpret_cast<float*>(base) + idx, a, b, c, d);
+  else *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(a, b, c, d);
+}
+
 // ---------------------------------------------------------------- GEMM epilogues
 // Every GEMM computes acc[m][n] = sum_k A[m][k] * Bw[n][k]  (both operands K-major, i.e. torch Linear).
 enum EpiMode : int {
@@ -82,7 +125,7 @@ enum EpiMode : int {
 struct EpiParams {
   int M, N;           // logical extents of acc
   const float* bias;  // LINEAR/QK/GLU: [N]; VT: [M]; may be null (LINEAR, POS)
-  float* out;         // LINEAR / GLU / POS destination
+  void* out;          // LINEAR / GLU / POS destination: fp32, or operand-typed when round_out != 0
   long ldo;           // LINEAR / GLU row stride of out
   const float* resid; // LINEAR: optional residual (same layout as out; may alias out)
   float alpha;        // LINEAR: scale of the residual branch
@@ -91,21 +134,29 @@ struct EpiParams {
   int T, H, Tp, Rp;   // frames per utterance, heads, padded T of v^T, padded rows of the pos table
   const float* pos_u; // QK: [H*64]
   const float* pos_v;
-  float* qu;
-  float* qv;
-  float* kk;
-  float* vt;
+  void* qu;           // operand-typed (float for OP_F32/OP_TF32, __half for OP_F16)
+  void* qv;
+  void* kk;
+  void* vt;
 };
 
-template <int MODE>
+// scalar store of one operand-or-fp32 value: `operand` says the destination is TOp-typed (rounded), else plain fp32
+template <typename TOp>
+__device__ __forceinline__ void put(void* base, long idx, float v, bool operand) {
+  if (operand) store_op1<TOp>(reinterpret_cast<TOp*>(base) + idx, v);
+  else reinterpret_cast<float*>(base)[idx] = v;
+}
+
+// Scalar (one element) epilogue: used by the CUDA-core GEMM and by the tensor-core kernel's ragged edges.
+// TOp = float serves OP_F32 (round_out = 0) and OP_TF32 (round_out = 1); TOp = __half serves OP_F16.
+template <int MODE, typename TOp = float>
 __device__ __forceinline__ void epi_store(const EpiParams& p, int m, int n, float acc) {
   if (m >= p.M || n >= p.N) return;
   if constexpr (MODE == EPI_LINEAR) {
     float v = acc + (p.bias ? p.bias[n] : 0.0f);
     if (p.relu) v = fmaxf(v, 0.0f);
     if (p.resid) v = p.resid[(long)m * p.ldo + n] + p.alpha * v;
-    if (p.round_out) v = round_tf32(v);
-    p.out[(long)m * p.ldo + n] = v;
+    put<TOp>(p.out, (long)m * p.ldo + n, v, p.round_out != 0);
   } else if constexpr (MODE == EPI_QK) {
     const int D = p.H * kHeadDim;
     const int b = m / p.T, t = m - b * p.T;
@@ -114,51 +165,47 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, int m, int n, floa
     const long idx = (((long)b * p.H + h) * p.T + t) * kHeadDim + d;
     const float v = acc + p.bias[n];
     if (n < D) {
-      float a = v + p.pos_u[nn], c = v + p.pos_v[nn];
-      if (p.round_out) { a = round_tf32(a); c = round_tf32(c); }
-      p.qu[idx] = a;
-      p.qv[idx] = c;
+      put<TOp>(p.qu, idx, v + p.pos_u[nn], p.round_out != 0);
+      put<TOp>(p.qv, idx, v + p.pos_v[nn], p.round_out != 0);
     } else {
-      p.kk[idx] = p.round_out ? round_tf32(v) : v;
+      put<TOp>(p.kk, idx, v, p.round_out != 0);
     }
   } else if constexpr (MODE == EPI_VT) {
     const int b = n / p.T, t = n - b * p.T;
     const int h = m / kHeadDim, d = m - h * kHeadDim;
-    float v = acc + p.bias[m];
-    if (p.round_out) v = round_tf32(v);
-    p.vt[(((long)b * p.H + h) * kHeadDim + d) * p.Tp + t] = v;
+    put<TOp>(p.vt, (((long)b * p.H + h) * kHeadDim + d) * p.Tp + t, acc + p.bias[m], p.round_out != 0);
   } else if constexpr (MODE == EPI_POS) {
     const int D = p.H * kHeadDim;
     const int l = n / D, r = n - l * D;
     const int h = r / kHeadDim, d = r - h * kHeadDim;
-    float v = acc;
-    if (p.round_out) v = round_tf32(v);
-    p.out[(((long)l * p.H + h) * p.Rp + m) * kHeadDim + d] = v;
+    put<TOp>(p.out, (((long)l * p.H + h) * p.Rp + m) * kHeadDim + d, acc, p.round_out != 0);
   }
 }
 
-// GLU pair: n_val is the interleaved column of the value half, the gate sits 64 columns further.
+// GLU pair: n_val is the interleaved column of the value half, the gate sits 64 columns further.  Output is fp32
+// (it feeds the depthwise conv, not a tensor-core operand).
 __device__ __forceinline__ void epi_store_glu(const EpiParams& p, int m, int n_val, float acc_val, float acc_gate) {
   if (m >= p.M || n_val + 64 >= p.N) return;
   const float a = acc_val + p.bias[n_val];
   const float g = acc_gate + p.bias[n_val + 64];
   const int c = (n_val >> 7) * 64 + (n_val & 63);
-  p.out[(long)m * p.ldo + c] = a * sigmoidf_acc(g);
+  reinterpret_cast<float*>(p.out)[(long)m * p.ldo + c] = a * sigmoidf_acc(g);
 }
 
 // ---------------------------------------------------------------- kernel launchers (defined in the .cu files)
 // fp32 CUDA-core GEMM (gemm_simt.cu)
 int gemm_simt(int mode, const float* A, const float* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
-// tcgen05 TF32 GEMM (gemm_tc.cu)
-int gemm_tc(int mode, const float* A, const float* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+// tcgen05 GEMM (gemm_tc.cu); opk = OP_TF32 (A, Bw are float) or OP_F16 (A, Bw are __half)
+int gemm_tc(int mode, int opk, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 
 // elementwise.cu
 int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStream_t st);
-int launch_layernorm(const float* x, const float* g, const float* b, float* y, int rows, int d, int round_out,
+// `out_kind` is an OperandKind: how y / pe is stored
+int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st);
-int launch_sinusoid(float* pe, int T, int d, int round_out, cudaStream_t st);
-int launch_dwconv_bn_silu(const float* x, const float* wt /*(K,C)*/, const float* scale, const float* shift, float* y,
-                          int B, int T, int C, int K, int round_out, cudaStream_t st);
+int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st);
+int launch_dwconv_bn_silu(const float* x, const float* wt /*(K,C)*/, const float* scale, const float* shift, void* y,
+                          int B, int T, int C, int K, int out_kind, cudaStream_t st);
 
 // attention: q-side tensors (B,H,T,64), vt (B,H,64,Tp), pos (H,Rp,64) for one layer, ctx (B*T, H*64)
 int attention_simt(const float* qu, const float* qv, const float* kk, const float* vt, const float* pos,
@@ -167,5 +214,8 @@ int attention_simt(const float* qu, const float* qv, const float* kk, const floa
 int attention_tc(const float* qu, const float* qv, const float* kk, const float* vt, const float* pos,
                  const int32_t* lengths, float* ctx, int B, int T, int H, int Tp, int Rp, int round_out,
                  cudaStream_t st);
+// fp16 operands (attention_f16.cu): same layouts with __half elements, Tp a multiple of 8; ctx stored as __half
+int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vt, const __half* pos,
+                  const int32_t* lengths, __half* ctx, int B, int T, int H, int Tp, int Rp, cudaStream_t st);
 
 }  // namespace avsr

@@ -33,13 +33,12 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float* __restrict__ y,
-                                                        int rows, int d, int round_out) {
+                                                        const float* __restrict__ beta, void* __restrict__ y,
+                                                        int rows, int d, int out_kind) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
-  float4* yr = reinterpret_cast<float4*>(y + (long)warp * d);
   const int nvec = d >> 2;
   float4 v[kLnMaxVec];
   float s = 0.f;
@@ -74,19 +73,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      yr[c] = o;
+      store_kind4(y, (long)warp * d + 4 * c, out_kind, o.x, o.y, o.z, o.w);
     }
   }
 }
 
-int launch_layernorm(const float* x, const float* g, const float* b, float* y, int rows, int d, int round_out,
+int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st) {
   AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                kLnMaxVec * 128);
   if (rows <= 0) return AVSR_OK;
   const int warps_per_block = 8;
-  layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, st>>>(x, g, b, y, rows, d, round_out);
+  layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, st>>>(x, g, b, y, rows, d, out_kind);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
@@ -95,7 +93,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, float* y, i
 // Row m <-> rel = T-1-m; even channels sin(rel*w_i), odd channels cos(rel*w_i), w_i = exp(2i * -(ln 1e4 / d)).
 // The reference evaluates everything in fp32: the frequency is a correctly rounded fp32 exp, the
 // argument an fp32 product; sinf/cosf here take the full-range (non fast-math) path.
-__global__ void sinusoid_kernel(float* __restrict__ pe, int T, int d, int round_out) {
+__global__ void sinusoid_kernel(void* __restrict__ pe, int T, int d, int out_kind) {
   const int half = d >> 1;
   const long total = (long)(2 * T - 1) * half;
   const float step = (float)(-(log(10000.0) / (double)d));
@@ -106,18 +104,24 @@ __global__ void sinusoid_kernel(float* __restrict__ pe, int T, int d, int round_
     const int rel = T - 1 - m;
     float arg = fabsf((float)rel) * inv;
     if (rel < 0) arg = -arg;
-    float s = sinf(arg), co = cosf(arg);
-    if (round_out) { s = round_tf32(s); co = round_tf32(co); }
-    reinterpret_cast<float2*>(pe + (long)m * d)[c] = make_float2(s, co);
+    const float s = sinf(arg), co = cosf(arg);
+    const long idx = (long)m * d + 2 * c;
+    if (out_kind == OP_F16) {
+      *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(pe) + idx) = __halves2half2(to_half_sat(s), to_half_sat(co));
+    } else if (out_kind == OP_TF32) {
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(pe) + idx) = make_float2(round_tf32(s), round_tf32(co));
+    } else {
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(pe) + idx) = make_float2(s, co);
+    }
   }
 }
 
-int launch_sinusoid(float* pe, int T, int d, int round_out, cudaStream_t st) {
+int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st) {
   AVSR_REQUIRE(T > 0 && d > 0 && d % 2 == 0, "sinusoid: bad T=%d d=%d", T, d);
   const long total = (long)(2 * T - 1) * (d / 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sinusoid_kernel<<<blocks, 256, 0, st>>>(pe, T, d, round_out);
+  sinusoid_kernel<<<blocks, 256, 0, st>>>(pe, T, d, out_kind);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
@@ -133,8 +137,8 @@ constexpr int kDwTT = 32;
 
 __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt,
                                                              const float* __restrict__ scale,
-                                                             const float* __restrict__ shift, float* __restrict__ y,
-                                                             int T, int C, int K, int round_out) {
+                                                             const float* __restrict__ shift, void* __restrict__ y,
+                                                             int T, int C, int K, int out_kind) {
   extern __shared__ float4 dw_smem[];
   const int rows_in = kDwTT + K - 1;
   float4* in_s = dw_smem;                          // [rows_in][16]
@@ -180,22 +184,21 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __rest
     float4 o;
     o.x = fmaf(a.x, sc.x, sh.x); o.y = fmaf(a.y, sc.y, sh.y); o.z = fmaf(a.z, sc.z, sh.z); o.w = fmaf(a.w, sc.w, sh.w);
     o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
-    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    *reinterpret_cast<float4*>(y + ((long)b * T + t) * C + c) = o;
+    store_kind4(y, ((long)b * T + t) * C + c, out_kind, o.x, o.y, o.z, o.w);
   };
   finish(a0, t0 + ts);
   finish(a1, t0 + ts + 16);
 }
 
-int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, float* y, int B,
-                          int T, int C, int K, int round_out, cudaStream_t st) {
+int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, void* y, int B,
+                          int T, int C, int K, int out_kind, cudaStream_t st) {
   AVSR_REQUIRE(C % 4 == 0 && K % 2 == 1 && K >= 1 && K <= 255, "dwconv: C=%d must be a multiple of 4, K=%d odd", C, K);
   if (B <= 0 || T <= 0) return AVSR_OK;
   const size_t smem = (size_t)(kDwTT + K - 1 + K) * (kDwCh / 4) * sizeof(float4);
   if (smem > 48 * 1024)
     AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(C, kDwCh), cdiv(T, kDwTT), B);
-  dwconv_bn_silu_kernel<<<grid, 256, smem, st>>>(x, wt, scale, shift, y, T, C, K, round_out);
+  dwconv_bn_silu_kernel<<<grid, 256, smem, st>>>(x, wt, scale, shift, y, T, C, K, out_kind);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }

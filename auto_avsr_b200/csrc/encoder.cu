@@ -87,21 +87,24 @@ static int check_cfg(const AvsrEncoderConfig* c) {
 }
 
 // ------------------------------------------------------------------ preparation kernels
-__global__ void copy_round_kernel(const float* __restrict__ src, float* __restrict__ dst, long n, int round_out) {
+// copy with conversion to an operand storage kind (OP_F32 plain copy, OP_TF32 rounded fp32, OP_F16 half)
+__global__ void copy_round_kernel(const float* __restrict__ src, void* __restrict__ dst, long n, int kind) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float v = src[i];
-    dst[i] = round_out ? round_tf32(v) : v;
+    if (kind == OP_F16) reinterpret_cast<__half*>(dst)[i] = to_half_sat(v);
+    else reinterpret_cast<float*>(dst)[i] = kind == OP_TF32 ? round_tf32(v) : v;
   }
 }
 // pointwise_cov1 (2D, D[,1]) -> rows interleaved in groups of 64: [g*128, +64) value channels g*64.., then their gates
-__global__ void glu_interleave_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wo,
-                                      float* __restrict__ bo, int D, int round_out) {
+__global__ void glu_interleave_kernel(const float* __restrict__ w, const float* __restrict__ b, void* __restrict__ wo,
+                                      float* __restrict__ bo, int D, int kind) {
   const int r = blockIdx.x;  // destination row in [0, 2D)
   const int g = r >> 7, wi = r & 127;
   const int src = wi < 64 ? g * 64 + wi : D + g * 64 + (wi - 64);
   for (int k = threadIdx.x; k < D; k += blockDim.x) {
     const float v = w[(long)src * D + k];
-    wo[(long)r * D + k] = round_out ? round_tf32(v) : v;
+    if (kind == OP_F16) reinterpret_cast<__half*>(wo)[(long)r * D + k] = to_half_sat(v);
+    else reinterpret_cast<float*>(wo)[(long)r * D + k] = kind == OP_TF32 ? round_tf32(v) : v;
   }
   if (threadIdx.x == 0) bo[r] = b[src];
 }
@@ -118,12 +121,26 @@ __global__ void dw_fold_kernel(const float* __restrict__ w, const float* __restr
   shift[c] = bn_b[c] + (b[c] - mean[c]) * s;
 }
 
-static int copy_round(const float* src, float* dst, long n, int round_out, cudaStream_t st) {
+static int copy_round(const float* src, void* dst, long n, int kind, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  copy_round_kernel<<<blocks, 256, 0, st>>>(src, dst, n, round_out);
+  copy_round_kernel<<<blocks, 256, 0, st>>>(src, dst, n, kind);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
+}
+
+// ------------------------------------------------------------------ precision -> operand storage
+static inline bool valid_precision(int p) { return p == AVSR_PREC_FP32 || p == AVSR_PREC_TF32 || p == AVSR_PREC_F16; }
+static inline int operand_kind(int precision) {
+  return precision == AVSR_PREC_F16 ? OP_F16 : (precision == AVSR_PREC_TF32 ? OP_TF32 : OP_F32);
+}
+static inline size_t operand_size(int precision) { return precision == AVSR_PREC_F16 ? 2 : 4; }
+// element offset into an operand-typed buffer carved as floats
+static inline void* op_offset(void* base, size_t elems, int precision) {
+  return reinterpret_cast<char*>(base) + elems * operand_size(precision);
+}
+static inline const void* op_offset(const void* base, size_t elems, int precision) {
+  return reinterpret_cast<const char*>(base) + elems * operand_size(precision);
 }
 
 // ------------------------------------------------------------------ workspace
@@ -138,7 +155,7 @@ static Workspace layout_workspace(const AvsrEncoderConfig& c, int B, int T, void
   Workspace W;
   Carver cv{reinterpret_cast<char*>(base)};
   const size_t N = (size_t)B * T, D = c.d_model, F = c.linear_units;
-  W.Tp = (T + 3) & ~3;
+  W.Tp = (T + 7) & ~7;   // v^T rows 16-byte aligned for TMA with 2-byte elements too
   W.Rp = 2 * T - 1;
   W.x = cv.take(N * D); W.xn = cv.take(N * D); W.hid = cv.take(N * F);
   W.qu = cv.take(N * D); W.qv = cv.take(N * D); W.kk = cv.take(N * D);
@@ -157,7 +174,7 @@ __global__ void fill_lengths_kernel(int32_t* dst, const int32_t* src, int B, int
 }
 
 // ------------------------------------------------------------------ forward schedule
-static EpiParams epi_linear(int M, int N, const float* bias, float* out, const float* resid, float alpha, int relu,
+static EpiParams epi_linear(int M, int N, const float* bias, void* out, const float* resid, float alpha, int relu,
                             int round_out) {
   EpiParams e{};
   e.M = M; e.N = N; e.bias = bias; e.out = out; e.ldo = N; e.resid = resid; e.alpha = alpha; e.relu = relu;
@@ -165,23 +182,26 @@ static EpiParams epi_linear(int M, int N, const float* bias, float* out, const f
   return e;
 }
 
-static int run_gemm(int prec, int mode, const float* A, const float* Bw, int M, int N, int K, const EpiParams& e,
+static int run_gemm(int prec, int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& e,
                     cudaStream_t st) {
-  return prec == AVSR_PREC_TF32 ? gemm_tc(mode, A, Bw, M, N, K, e, st) : gemm_simt(mode, A, Bw, M, N, K, e, st);
+  if (prec == AVSR_PREC_FP32)
+    return gemm_simt(mode, reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(Bw), M, N, K, e, st);
+  return gemm_tc(mode, operand_kind(prec), A, Bw, M, N, K, e, st);
 }
 
 // the part of the forward that only touches workspace buffers (what a plan captures into its graph)
 static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int B, int T,
                         const int32_t* lengths, float* taps, int prec, cudaStream_t st) {
   const int N = B * T, D = c.d_model, F = c.linear_units, H = c.n_heads, L = c.num_blocks;
-  const int rnd = prec == AVSR_PREC_TF32 ? 1 : 0;
+  const int opk = operand_kind(prec);           // storage of every tensor that feeds a contraction
+  const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
   const size_t stage_bytes = (size_t)N * D * sizeof(float);
 
   // pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
-  AVSR_TRY(launch_sinusoid(W.pe, T, D, rnd, st));
+  AVSR_TRY(launch_sinusoid(W.pe, T, D, opk, st));
   {
     EpiParams e{};
-    e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = rnd;
+    e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = opr;
     AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, st));
   }
   if (W.Tp != T) AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
@@ -194,47 +214,50 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       return AVSR_OK;
     };
     // (1) macaron FFN: x += 0.5 * w2(relu(w1 LN(x)))                         conformer_encoder.py:110-116
-    AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, rnd, st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, rnd), st));
+    AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, opr), st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_linear(N, D, w.ffm_b2, W.x, W.x, 0.5f, 0, 0), st));
     AVSR_TRY(tap(0));
     // (2) rel-pos MHA: x += out(attn(LN(x)))                                  conformer_encoder.py:119-142
-    AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, rnd, st));
+    AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st));
     {
       EpiParams e{};
       e.M = N; e.N = 2 * D; e.bias = w.qk_b; e.T = T; e.H = H; e.pos_u = w.pos_u; e.pos_v = w.pos_v;
-      e.qu = W.qu; e.qv = W.qv; e.kk = W.kk; e.round_out = rnd;
+      e.qu = W.qu; e.qv = W.qv; e.kk = W.kk; e.round_out = opr;
       AVSR_TRY(run_gemm(prec, EPI_QK, W.xn, w.qk_w, N, 2 * D, D, e, st));
       EpiParams v{};
-      v.M = D; v.N = N; v.bias = w.v_b; v.T = T; v.H = H; v.Tp = W.Tp; v.vt = W.vt; v.round_out = rnd;
+      v.M = D; v.N = N; v.bias = w.v_b; v.T = T; v.H = H; v.Tp = W.Tp; v.vt = W.vt; v.round_out = opr;
       AVSR_TRY(run_gemm(prec, EPI_VT, w.v_w, W.xn, D, N, D, v, st));
     }
     {
-      const float* pos_l = W.pos + (size_t)l * H * W.Rp * kHeadDim;
-      if (prec == AVSR_PREC_TF32)
-        AVSR_TRY(attention_tc(W.qu, W.qv, W.kk, W.vt, pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, rnd, st));
+      const void* pos_l = op_offset(W.pos, (size_t)l * H * W.Rp * kHeadDim, prec);
+      if (prec == AVSR_PREC_F16)
+        AVSR_TRY(attention_f16((const __half*)W.qu, (const __half*)W.qv, (const __half*)W.kk, (const __half*)W.vt,
+                               (const __half*)pos_l, lengths, (__half*)W.ctx, B, T, H, W.Tp, W.Rp, st));
+      else if (prec == AVSR_PREC_TF32)
+        AVSR_TRY(attention_tc(W.qu, W.qv, W.kk, W.vt, (const float*)pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, 1, st));
       else
-        AVSR_TRY(attention_simt(W.qu, W.qv, W.kk, W.vt, pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, rnd, st));
+        AVSR_TRY(attention_simt(W.qu, W.qv, W.kk, W.vt, (const float*)pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, 0, st));
     }
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.ctx, w.out_w, N, D, D, epi_linear(N, D, w.out_b, W.x, W.x, 1.0f, 0, 0), st));
     AVSR_TRY(tap(1));
     // (3) conv module: x += pw2(silu(bn(dw(glu(pw1 LN(x))))))                 conformer_encoder.py:145-151, :30-35
-    AVSR_TRY(launch_layernorm(W.x, w.ln_conv_w, w.ln_conv_b, W.xn, N, D, rnd, st));
+    AVSR_TRY(launch_layernorm(W.x, w.ln_conv_w, w.ln_conv_b, W.xn, N, D, opk, st));
     {
       EpiParams e{};
       e.M = N; e.N = 2 * D; e.bias = w.pw1_b; e.out = W.glu; e.ldo = D;
       AVSR_TRY(run_gemm(prec, EPI_GLU, W.xn, w.pw1_w, N, 2 * D, D, e, st));
     }
-    AVSR_TRY(launch_dwconv_bn_silu(W.glu, w.dw_wt, w.dw_scale, w.dw_shift, W.dw, B, T, D, c.cnn_kernel, rnd, st));
+    AVSR_TRY(launch_dwconv_bn_silu(W.glu, w.dw_wt, w.dw_scale, w.dw_shift, W.dw, B, T, D, c.cnn_kernel, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.dw, w.pw2_w, N, D, D, epi_linear(N, D, w.pw2_b, W.x, W.x, 1.0f, 0, 0), st));
     AVSR_TRY(tap(2));
     // (4) FFN: x += 0.5 * w2(relu(w1 LN(x)))                                  conformer_encoder.py:154-159
-    AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, rnd, st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, rnd), st));
+    AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, opk, st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, opr), st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_linear(N, D, w.ff_b2, W.x, W.x, 0.5f, 0, 0), st));
     AVSR_TRY(tap(3));
     // (5) x = LN_final(x)                                                     conformer_encoder.py:161-162
-    AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, 0, st));
+    AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st));
     AVSR_TRY(tap(4));
   }
   return AVSR_OK;
@@ -244,7 +267,7 @@ static int forward_impl(const AvsrEncoderConfig* cfg, const void* prepared, cons
                         int B, int T, float* out, float* taps, void* workspace, size_t workspace_bytes, int precision,
                         void* stream) {
   AVSR_TRY(check_cfg(cfg));
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   AVSR_REQUIRE(B >= 0 && T >= 0, "bad B=%d T=%d", B, T);
   if (B == 0 || T == 0) return AVSR_OK;  // empty batch: nothing to do
   AVSR_REQUIRE(prepared && xs && out && workspace, "NULL buffer");
@@ -292,14 +315,14 @@ int avsr_prepare_weights(const AvsrEncoderConfig* cfg, const AvsrLayerParams* la
                          void* stream) {
   AVSR_TRY(check_cfg(cfg));
   AVSR_REQUIRE(layers && after_norm_w && after_norm_b && prepared, "NULL argument");
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   Prepared P = layout_prepared(*cfg, prepared);
   if (P.bytes > prepared_bytes) {
     set_error("prepared buffer too small: need %zu bytes, got %zu", P.bytes, prepared_bytes);
     return AVSR_E_WORKSPACE;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rnd = precision == AVSR_PREC_TF32;
+  const int rnd = operand_kind(precision);   // storage kind of the GEMM weights
   const long D = cfg->d_model, F = cfg->linear_units, K = cfg->cnn_kernel;
   for (int l = 0; l < cfg->num_blocks; ++l) {
     const AvsrLayerParams& s = layers[l];
@@ -310,7 +333,7 @@ int avsr_prepare_weights(const AvsrEncoderConfig* cfg, const AvsrLayerParams* la
     AVSR_TRY(copy_round(s.ffm_w1, d.ffm_w1, F * D, rnd, st)); AVSR_TRY(copy_round(s.ffm_b1, d.ffm_b1, F, 0, st));
     AVSR_TRY(copy_round(s.ffm_w2, d.ffm_w2, D * F, rnd, st)); AVSR_TRY(copy_round(s.ffm_b2, d.ffm_b2, D, 0, st));
     AVSR_TRY(copy_round(s.norm_ffm_w, d.ln_ffm_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_ffm_b, d.ln_ffm_b, D, 0, st));
-    AVSR_TRY(copy_round(s.q_w, d.qk_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.k_w, d.qk_w + D * D, D * D, rnd, st));
+    AVSR_TRY(copy_round(s.q_w, d.qk_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.k_w, op_offset(d.qk_w, (size_t)D * D, precision), D * D, rnd, st));
     AVSR_TRY(copy_round(s.q_b, d.qk_b, D, 0, st)); AVSR_TRY(copy_round(s.k_b, d.qk_b + D, D, 0, st));
     AVSR_TRY(copy_round(s.v_w, d.v_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.v_b, d.v_b, D, 0, st));
     AVSR_TRY(copy_round(s.out_w, d.out_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.out_b, d.out_b, D, 0, st));
@@ -327,7 +350,7 @@ int avsr_prepare_weights(const AvsrEncoderConfig* cfg, const AvsrLayerParams* la
     AVSR_TRY(copy_round(s.ff_w2, d.ff_w2, D * F, rnd, st)); AVSR_TRY(copy_round(s.ff_b2, d.ff_b2, D, 0, st));
     AVSR_TRY(copy_round(s.norm_ff_w, d.ln_ff_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_ff_b, d.ln_ff_b, D, 0, st));
     AVSR_TRY(copy_round(s.norm_final_w, d.ln_fin_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_final_b, d.ln_fin_b, D, 0, st));
-    AVSR_TRY(copy_round(s.pos_w, P.pos_w_all + (size_t)l * D * D, D * D, rnd, st));
+    AVSR_TRY(copy_round(s.pos_w, op_offset(P.pos_w_all, (size_t)l * D * D, precision), D * D, rnd, st));
   }
   AVSR_TRY(copy_round(after_norm_w, P.after_w, D, 0, st));
   AVSR_TRY(copy_round(after_norm_b, P.after_b, D, 0, st));
@@ -357,7 +380,7 @@ int avsr_plan_create(const AvsrEncoderConfig* cfg, const void* prepared, int B, 
   AVSR_TRY(check_cfg(cfg));
   AVSR_REQUIRE(plan && prepared && workspace, "NULL argument");
   AVSR_REQUIRE(B > 0 && T > 0, "plan needs B>0, T>0 (got %d, %d)", B, T);
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   Workspace W = layout_workspace(*cfg, B, T, workspace);
   if (W.bytes > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", W.bytes, workspace_bytes);
@@ -435,41 +458,74 @@ int avsr_layernorm(const float* x, const float* gamma, const float* beta, float*
   return launch_layernorm(x, gamma, beta, y, rows, d, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t avsr_linear_workspace_bytes(int rows, int n, int k, int precision) {
+  if (precision != AVSR_PREC_F16 || rows <= 0 || n <= 0 || k <= 0) return 16;
+  return align_up((size_t)rows * k * 2, 256) + align_up((size_t)n * k * 2, 256);
+}
+
 int avsr_linear(const float* x, const float* w, const float* bias, const float* resid, float alpha, int relu, float* y,
-                int rows, int n, int k, int precision, void* stream) {
+                int rows, int n, int k, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   AVSR_REQUIRE(x && w && y, "NULL argument");
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const void *xa = x, *wa = w;
+  if (precision == AVSR_PREC_F16 && rows > 0 && n > 0) {
+    AVSR_REQUIRE(workspace != nullptr, "avsr_linear: AVSR_PREC_F16 needs a workspace");
+    if (avsr_linear_workspace_bytes(rows, n, k, precision) > workspace_bytes) {
+      set_error("linear workspace too small: need %zu bytes, got %zu", avsr_linear_workspace_bytes(rows, n, k, precision),
+                workspace_bytes);
+      return AVSR_E_WORKSPACE;
+    }
+    char* xh = reinterpret_cast<char*>(workspace);
+    char* wh = xh + align_up((size_t)rows * k * 2, 256);
+    AVSR_TRY(copy_round(x, xh, (long)rows * k, OP_F16, st));
+    AVSR_TRY(copy_round(w, wh, (long)n * k, OP_F16, st));
+    xa = xh; wa = wh;
+  }
   // note: in TF32 mode operands are used as given (the tensor core truncates fp32 -> tf32)
-  return run_gemm(precision, EPI_LINEAR, x, w, rows, n, k, epi_linear(rows, n, bias, y, resid, alpha, relu, 0),
+  return run_gemm(precision, EPI_LINEAR, xa, wa, rows, n, k, epi_linear(rows, n, bias, y, resid, alpha, relu, 0), st);
+}
+
+int avsr_linear_operands(const void* x_op, const void* w_op, const float* bias, void* y_op, int rows, int n, int k,
+                         int relu, int precision, void* stream) {
+  AVSR_REQUIRE(x_op && w_op && y_op, "NULL argument");
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  return run_gemm(precision, EPI_LINEAR, x_op, w_op, rows, n, k,
+                  epi_linear(rows, n, bias, reinterpret_cast<float*>(y_op), nullptr, 0.f, relu, precision != AVSR_PREC_FP32),
                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 // (B,T,H*64) -> (B,H,T,64) with optional per-channel bias add; or -> (B,H,64,Tp) when transpose != 0
-__global__ void split_heads_kernel(const float* __restrict__ src, const float* __restrict__ bias, float* __restrict__ dst,
-                                   int B, int T, int H, int Tp, int transpose, int round_out) {
+__global__ void split_heads_kernel(const float* __restrict__ src, const float* __restrict__ bias, void* __restrict__ dst,
+                                   int B, int T, int H, int Tp, int transpose, int kind) {
   const long total = (long)B * T * H * kHeadDim;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (H * kHeadDim));
     const long r = i / (H * kHeadDim);
     const int b = (int)(r / T), t = (int)(r % T), h = c / kHeadDim, d = c % kHeadDim;
-    float v = src[i] + (bias ? bias[c] : 0.f);
-    if (round_out) v = round_tf32(v);
-    if (transpose) dst[(((long)b * H + h) * kHeadDim + d) * Tp + t] = v;
-    else dst[(((long)b * H + h) * T + t) * kHeadDim + d] = v;
+    const float v = src[i] + (bias ? bias[c] : 0.f);
+    const long o = transpose ? (((long)b * H + h) * kHeadDim + d) * Tp + t : (((long)b * H + h) * T + t) * kHeadDim + d;
+    if (kind == OP_F16) reinterpret_cast<__half*>(dst)[o] = to_half_sat(v);
+    else reinterpret_cast<float*>(dst)[o] = kind == OP_TF32 ? round_tf32(v) : v;
   }
+}
+
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = __half2float(src[i]);
 }
 
 size_t avsr_attention_workspace_bytes(int B, int T, int H) {
   if (B <= 0 || T <= 0 || H <= 0) return 256;
-  const size_t N = (size_t)B * T, D = (size_t)H * kHeadDim, Tp = (T + 3) & ~3;
-  return 3 * align_up(N * D * 4, 256) + align_up((size_t)B * D * Tp * 4, 256) + align_up((size_t)(2 * T - 1) * D * 4, 256);
+  const size_t N = (size_t)B * T, D = (size_t)H * kHeadDim, Tp = (T + 7) & ~7;
+  return 4 * align_up(N * D * 4, 256) + align_up((size_t)B * D * Tp * 4, 256) + align_up((size_t)(2 * T - 1) * D * 4, 256);
 }
 
 int avsr_relpos_attention(const float* q, const float* k, const float* v, const float* p, const float* pos_bias_u,
                           const float* pos_bias_v, const int32_t* lengths, float* ctx, int B, int T, int H,
                           void* workspace, size_t workspace_bytes, int precision, void* stream) {
   AVSR_REQUIRE(q && k && v && p && pos_bias_u && pos_bias_v && ctx && workspace, "NULL argument");
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   if (B <= 0 || T <= 0) return AVSR_OK;
   if (avsr_attention_workspace_bytes(B, T, H) > workspace_bytes) {
     set_error("attention workspace too small: need %zu, got %zu", avsr_attention_workspace_bytes(B, T, H), workspace_bytes);
@@ -477,19 +533,26 @@ int avsr_relpos_attention(const float* q, const float* k, const float* v, const 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t N = (size_t)B * T, D = (size_t)H * kHeadDim;
-  const int Tp = (T + 3) & ~3, R = 2 * T - 1;
-  const int rnd = precision == AVSR_PREC_TF32;
+  const int Tp = (T + 7) & ~7, R = 2 * T - 1;
+  const int kind = operand_kind(precision);
   Carver cv{reinterpret_cast<char*>(workspace)};
   float *qu = cv.take(N * D), *qv = cv.take(N * D), *kk = cv.take(N * D), *vt = cv.take((size_t)B * D * Tp),
-        *pos = cv.take((size_t)R * D);
+        *pos = cv.take((size_t)R * D), *ctxh = cv.take(N * D);
   const int blocks = 148 * 4;
   if (Tp != T) AVSR_CUDA_TRY(cudaMemsetAsync(vt, 0, (size_t)B * D * Tp * sizeof(float), st));
-  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_u, qu, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
-  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_v, qv, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
-  split_heads_kernel<<<blocks, 256, 0, st>>>(k, nullptr, kk, B, T, H, Tp, 0, rnd); AVSR_CHECK_LAUNCH();
-  split_heads_kernel<<<blocks, 256, 0, st>>>(v, nullptr, vt, B, T, H, Tp, 1, rnd); AVSR_CHECK_LAUNCH();
-  split_heads_kernel<<<blocks, 256, 0, st>>>(p, nullptr, pos, 1, R, H, R, 0, rnd); AVSR_CHECK_LAUNCH();
-  if (rnd) return attention_tc(qu, qv, kk, vt, pos, lengths, ctx, B, T, H, Tp, R, 0, st);
+  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_u, qu, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_v, qv, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(k, nullptr, kk, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(v, nullptr, vt, B, T, H, Tp, 1, kind); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(p, nullptr, pos, 1, R, H, R, 0, kind); AVSR_CHECK_LAUNCH();
+  if (precision == AVSR_PREC_F16) {
+    AVSR_TRY(attention_f16((const __half*)qu, (const __half*)qv, (const __half*)kk, (const __half*)vt, (const __half*)pos,
+                           lengths, (__half*)ctxh, B, T, H, Tp, R, st));
+    half_to_float_kernel<<<blocks, 256, 0, st>>>((const __half*)ctxh, ctx, (long)N * D);
+    AVSR_CHECK_LAUNCH();
+    return AVSR_OK;
+  }
+  if (precision == AVSR_PREC_TF32) return attention_tc(qu, qv, kk, vt, pos, lengths, ctx, B, T, H, Tp, R, 0, st);
   return attention_simt(qu, qv, kk, vt, pos, lengths, ctx, B, T, H, Tp, R, 0, st);
 }
 
@@ -509,23 +572,36 @@ int avsr_dwconv_bn_silu(const float* x, const float* w, const float* b, const fl
   return launch_dwconv_bn_silu(x, wt, scale, shift, y, B, T, C, K, 0, st);
 }
 
+size_t avsr_pointwise_glu_workspace_bytes(int rows, int C) {
+  if (rows < 0 || C <= 0) return 16;
+  return align_up(((size_t)2 * C * C + 2 * C) * sizeof(float), 256) + align_up((size_t)rows * C * 2, 256);
+}
+
 int avsr_pointwise_glu(const float* x, const float* w, const float* b, float* y, int rows, int C, void* workspace,
                        size_t workspace_bytes, int precision, void* stream) {
   AVSR_REQUIRE(x && w && b && y && workspace, "NULL argument");
   AVSR_REQUIRE(C > 0 && C % 64 == 0, "pointwise_glu: C=%d must be a multiple of 64", C);
-  AVSR_REQUIRE(precision == AVSR_PREC_FP32 || precision == AVSR_PREC_TF32, "bad precision %d", precision);
-  const size_t need = ((size_t)2 * C * C + 2 * C) * sizeof(float);
-  if (need > workspace_bytes) {
-    set_error("pointwise_glu workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  if (avsr_pointwise_glu_workspace_bytes(rows, C) > workspace_bytes) {
+    set_error("pointwise_glu workspace too small: need %zu bytes, got %zu", avsr_pointwise_glu_workspace_bytes(rows, C),
+              workspace_bytes);
     return AVSR_E_WORKSPACE;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  float *wi = reinterpret_cast<float*>(workspace), *bi = wi + (size_t)2 * C * C;
-  glu_interleave_kernel<<<(unsigned)(2 * C), 256, 0, st>>>(w, b, wi, bi, C, 0);
+  float* wi = reinterpret_cast<float*>(workspace);
+  float* bi = wi + (size_t)2 * C * C;
+  char* xh = reinterpret_cast<char*>(workspace) + align_up(((size_t)2 * C * C + 2 * C) * sizeof(float), 256);
+  const int kind = precision == AVSR_PREC_F16 ? OP_F16 : OP_F32;   // TF32: the tensor core truncates raw fp32
+  glu_interleave_kernel<<<(unsigned)(2 * C), 256, 0, st>>>(w, b, wi, bi, C, kind);
   AVSR_CHECK_LAUNCH();
+  const void* xa = x;
+  if (precision == AVSR_PREC_F16 && rows > 0) {
+    AVSR_TRY(copy_round(x, xh, (long)rows * C, OP_F16, st));
+    xa = xh;
+  }
   EpiParams e{};
   e.M = rows; e.N = 2 * C; e.bias = bi; e.out = y; e.ldo = C;
-  return run_gemm(precision, EPI_GLU, x, wi, rows, 2 * C, C, e, st);
+  return run_gemm(precision, EPI_GLU, xa, wi, rows, 2 * C, C, e, st);
 }
 
 int avsr_rel_sinusoid_table(float* pe, int T, int d, void* stream) {

@@ -1,17 +1,18 @@
-// Tensor-core GEMM for the Conformer layer's seven projections (FFN x2, QK, V^T, out, pw1+GLU, pw2) and the
-// stacked linear_pos:   acc[m][n] = sum_k A[m][k] * Bw[n][k]   (both K-major = torch.nn.Linear layout).
+// Tensor-core GEMM for the Conformer layer's projections (FFN x2, QK, V^T, out, pw1+GLU, pw2) and the stacked
+// linear_pos:   acc[m][n] = sum_k A[m][k] * Bw[n][k]   (both K-major = torch.nn.Linear layout).
 //
-// Blackwell-native pipeline (sm_100a), one 128 x BN output tile per CTA, two CTAs resident per SM:
-//   warp 0  : TMA producer   -- cp.async.bulk.tensor 2-D boxes (128 x 32 fp32 = 128 B rows, SWIZZLE_128B) of A and
+// Blackwell-native pipeline (sm_100a).  One CTA owns a (MSUB*128) x BN output tile:
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D boxes (rows x 128 bytes, SWIZZLE_128B) of A (MSUB boxes) and
 //                               Bw into a STAGES-deep shared-memory ring, completion on `full` mbarriers
-//   warp 1  : MMA issuer     -- one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x4 per stage straight
-//                               from shared memory into a TMEM accumulator; tcgen05.commit releases the stage
+//   warp 1   : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BN, K=32 bytes) x4 x MSUB per stage straight
+//                               from shared memory into MSUB TMEM accumulators; tcgen05.commit releases the stage
 //                               (`empty` mbarrier) and finally signals `tmem_full`
-//   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fused epilogue (bias / ReLU / residual / GLU /
-//                               head-major scatter / TF32 rounding of the next operand), direct global stores
-// Out-of-bounds rows of the last M / N tile are zero-filled by TMA and masked in the epilogue.
-// Operands are fp32 in memory, pre-rounded to TF32 by their producers (avsr_prepare_weights, the LayerNorm /
-// epilogue that wrote them), so the tensor core's mantissa truncation is exact.
+//   warps 2-9: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fused epilogue (bias / ReLU / residual / GLU /
+//                               head-major scatter / conversion to the next operand's storage), direct global stores
+// Operand storage (template TOp): float = TF32 (kind::tf32, 8 elements per MMA-K) or __half (kind::f16, 16 per
+// MMA-K; same 10-bit mantissa, half the bytes, twice the rate).  Out-of-bounds rows of edge tiles are zero-filled
+// by TMA and masked in the epilogue.  With fp32/fp16 operands this GEMM is L2->SM bandwidth bound at M = 1600
+// rows, so the tile shape is chosen per problem by a small cost model (bytes through L2 vs tensor-pipe time).
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -36,49 +37,51 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-int make_tmap_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 int esz) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return AVSR_E_CUDA; }
-  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0 && box_rows <= 256,
-               "tensor map: base/stride must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
+  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * esz) % 16 == 0 && box_rows <= 256 &&
+                   (esz == 4 || esz == 2),
+               "tensor map: base/stride must be 16-byte aligned (ld=%llu, esz=%d)", (unsigned long long)ld, esz);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {32, box_rows};
+  cuuint64_t gstr[1] = {ld * (uint64_t)esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: CUresult %d", (int)r); return AVSR_E_CUDA; }
   return AVSR_OK;
 }
 
-int make_tmap_3d(CUtensorMap* map, const float* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld_row,
-                 uint64_t ld_plane, uint32_t box_rows) {
+int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld_row,
+                 uint64_t ld_plane, uint32_t box_rows, int esz) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return AVSR_E_CUDA; }
-  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_row * 4) % 16 == 0 && (ld_plane * 4) % 16 == 0 &&
-                   box_rows <= 256,
+  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_row * esz) % 16 == 0 &&
+                   (ld_plane * esz) % 16 == 0 && box_rows <= 256 && (esz == 4 || esz == 2),
                "tensor map 3d: base/strides must be 16-byte aligned");
   cuuint64_t gdim[3] = {cols, rows, planes};
-  cuuint64_t gstr[2] = {ld_row * sizeof(float), ld_plane * sizeof(float)};
-  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint64_t gstr[2] = {ld_row * (uint64_t)esz, ld_plane * (uint64_t)esz};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esz), box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r); return AVSR_E_CUDA; }
   return AVSR_OK;
 }
 
 // ---------------------------------------------------------------- vectorised epilogues: one row, 32 columns
-// `v` holds acc[m][n .. n+31]; n is a multiple of 32 inside the tile.
-template <int MODE>
+// `v` holds acc[m][n .. n+31]; n is a multiple of 32.  TOp is the storage type of operand-typed destinations.
+template <int MODE, typename TOp>
 __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int m, int n, const float* v) {
   if (m >= p.M || n >= p.N) return;
   if constexpr (MODE == EPI_LINEAR) {
     if (n + 32 <= p.N && (p.ldo & 3) == 0) {
-      float* dst = p.out + (long)m * p.ldo + n;
-      const float* res = p.resid ? p.resid + (long)m * p.ldo + n : nullptr;
+      const long off = (long)m * p.ldo + n;
+      const float* res = p.resid ? p.resid + off : nullptr;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -91,12 +94,12 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int m, int n, co
           const float4 r = *reinterpret_cast<const float4*>(res + j);
           o.x = r.x + p.alpha * o.x; o.y = r.y + p.alpha * o.y; o.z = r.z + p.alpha * o.z; o.w = r.w + p.alpha * o.w;
         }
-        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        *reinterpret_cast<float4*>(dst + j) = o;
+        if (p.round_out) store_op4<TOp>(reinterpret_cast<TOp*>(p.out) + off + j, o.x, o.y, o.z, o.w);
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = o;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) epi_store<EPI_LINEAR>(p, m, n + j, v[j]);
+      for (int j = 0; j < 32; ++j) epi_store<EPI_LINEAR, TOp>(p, m, n + j, v[j]);
     }
   } else if constexpr (MODE == EPI_QK) {
     const int D = p.H * kHeadDim;                 // multiple of 64, so a 32-chunk never straddles q|k or a head
@@ -107,21 +110,14 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int m, int n, co
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
-      float4 o = make_float4(v[j] + bq.x, v[j + 1] + bq.y, v[j + 2] + bq.z, v[j + 3] + bq.w);
+      const float4 o = make_float4(v[j] + bq.x, v[j + 1] + bq.y, v[j + 2] + bq.z, v[j + 3] + bq.w);
       if (n < D) {
         const float4 u = *reinterpret_cast<const float4*>(p.pos_u + nn + j);
         const float4 w = *reinterpret_cast<const float4*>(p.pos_v + nn + j);
-        float4 a = make_float4(o.x + u.x, o.y + u.y, o.z + u.z, o.w + u.w);
-        float4 c = make_float4(o.x + w.x, o.y + w.y, o.z + w.z, o.w + w.w);
-        if (p.round_out) {
-          a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w);
-          c.x = round_tf32(c.x); c.y = round_tf32(c.y); c.z = round_tf32(c.z); c.w = round_tf32(c.w);
-        }
-        *reinterpret_cast<float4*>(p.qu + idx + j) = a;
-        *reinterpret_cast<float4*>(p.qv + idx + j) = c;
+        store_op4<TOp>(reinterpret_cast<TOp*>(p.qu) + idx + j, o.x + u.x, o.y + u.y, o.z + u.z, o.w + u.w);
+        store_op4<TOp>(reinterpret_cast<TOp*>(p.qv) + idx + j, o.x + w.x, o.y + w.y, o.z + w.z, o.w + w.w);
       } else {
-        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        *reinterpret_cast<float4*>(p.kk + idx + j) = o;
+        store_op4<TOp>(reinterpret_cast<TOp*>(p.kk) + idx + j, o.x, o.y, o.z, o.w);
       }
     }
   } else if constexpr (MODE == EPI_VT) {
@@ -130,36 +126,28 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& p, int m, int n, co
     const float bias = p.bias[m];
     const int b0 = n / p.T, t0 = n - b0 * p.T;
     if (t0 + 32 <= p.T && n + 32 <= p.N && (t0 & 3) == 0) {
-      float* dst = p.vt + (((long)b0 * p.H + h) * kHeadDim + d) * p.Tp + t0;
+      TOp* dst = reinterpret_cast<TOp*>(p.vt) + (((long)b0 * p.H + h) * kHeadDim + d) * p.Tp + t0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(v[j] + bias, v[j + 1] + bias, v[j + 2] + bias, v[j + 3] + bias);
-        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        *reinterpret_cast<float4*>(dst + j) = o;
-      }
+      for (int j = 0; j < 32; j += 4) store_op4<TOp>(dst + j, v[j] + bias, v[j + 1] + bias, v[j + 2] + bias, v[j + 3] + bias);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) epi_store<EPI_VT>(p, m, n + j, v[j]);
+      for (int j = 0; j < 32; ++j) epi_store<EPI_VT, TOp>(p, m, n + j, v[j]);
     }
   } else if constexpr (MODE == EPI_POS) {
     const int D = p.H * kHeadDim;
     const int l = n / D, r = n - l * D;
     const int h = r / kHeadDim, d0 = r - h * kHeadDim;
-    float* dst = p.out + (((long)l * p.H + h) * p.Rp + m) * kHeadDim + d0;
+    TOp* dst = reinterpret_cast<TOp*>(p.out) + (((long)l * p.H + h) * p.Rp + m) * kHeadDim + d0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      *reinterpret_cast<float4*>(dst + j) = o;
-    }
+    for (int j = 0; j < 32; j += 4) store_op4<TOp>(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
 }
 
-// GLU: value columns n .. n+31 (n % 128 < 64), gates 64 columns further; out column = (n/128)*64 + n%128
+// GLU: value columns n .. n+31 (n % 128 < 64), gates 64 columns further; out column = (n/128)*64 + n%128 (fp32)
 __device__ __forceinline__ void epi_chunk32_glu(const EpiParams& p, int m, int n, const float* val, const float* gate) {
   if (m >= p.M || n + 64 >= p.N) return;
   const int c0 = (n >> 7) * 64 + (n & 127);
-  float* dst = p.out + (long)m * p.ldo + c0;
+  float* dst = reinterpret_cast<float*>(p.out) + (long)m * p.ldo + c0;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 ba = *reinterpret_cast<const float4*>(p.bias + n + j);
@@ -174,24 +162,43 @@ __device__ __forceinline__ void epi_chunk32_glu(const EpiParams& p, int m, int n
 }
 
 // ---------------------------------------------------------------- the kernel
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;  // fp32 elements = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;          // rows per UMMA / per A box
+constexpr int TC_THREADS = 320;     // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
-template <int BN>
+template <int BN, int MSUB>
 struct TcCfg {
-  static constexpr int kStages = BN == 128 ? 3 : 4;
-  static constexpr int kABytes = TC_BM * TC_BK * 4;
-  static constexpr int kBBytes = BN * TC_BK * 4;
+  static constexpr int kABytes = MSUB * TC_BM * 128;
+  static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCtasPerSm = (MSUB == 1 && BN <= 128) ? 2 : 1;
+  static constexpr int kStagesFit = (TC_SMEM_BUDGET / kCtasPerSm) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kTmemCols = MSUB * BN;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "tile too large for shared memory");
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-template <int MODE, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <typename TOp> struct OpTraits;
+template <> struct OpTraits<float> {
+  static constexpr int kElemsPerBlock = 32;  // 128 bytes of fp32
+  __device__ static uint32_t idesc(int M, int N) { return umma_idesc_tf32(M, N); }
+  __device__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { mma_tf32(d, a, b, id, acc); }
+};
+template <> struct OpTraits<__half> {
+  static constexpr int kElemsPerBlock = 64;  // 128 bytes of fp16
+  __device__ static uint32_t idesc(int M, int N) { return umma_idesc_f16(M, N); }
+  __device__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { mma_f16(d, a, b, id, acc); }
+};
+
+template <int MODE, int BN, int MSUB, typename TOp>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MSUB>::kCtasPerSm)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, EpiParams ep) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MSUB>;
+  using Op = OpTraits<TOp>;
   constexpr int S = Cfg::kStages;
+  constexpr int KE = Op::kElemsPerBlock;
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -203,8 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_full_bar = bars + 8u * (2 * S);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int nkb = K / TC_BK;
+  const int m0 = blockIdx.y * (TC_BM * MSUB), n0 = blockIdx.x * BN;
+  const int nkb = K / KE;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -213,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -227,51 +234,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
         const uint32_t a_dst = base + s * Cfg::kStageBytes;
-        tma_load_2d(a_dst, &tmA, kb * TC_BK, m0, full_bar(s));
-        tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * TC_BK, n0, full_bar(s));
+#pragma unroll
+        for (int ms = 0; ms < MSUB; ++ms)
+          tma_load_2d(a_dst + ms * (TC_BM * 128), &tmA, kb * KE, m0 + ms * TC_BM, full_bar(s));
+        tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * KE, n0, full_bar(s));
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+      const uint32_t idesc = Op::idesc(TC_BM, BN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t a_addr = base + s * Cfg::kStageBytes;
-        const uint64_t a_desc = umma_desc_sw128(a_addr);
         const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k)  // 8 tf32 = 32 bytes = +2 in the descriptor's 16-byte address field
-          mma_tf32(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        for (int ms = 0; ms < MSUB; ++ms) {
+          const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
+            Op::mma(tmem_base + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        }
         tc_commit(empty_bar(s));
       }
       tc_commit(tmem_full_bar);
     }
   } else {
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
-    const int m = m0 + q * 32 + lane;
+    const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp drains
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if constexpr (MODE == EPI_GLU) {
-      static_assert(MODE != EPI_GLU || BN == 128, "GLU pairs live 64 columns apart inside a 128-wide tile");
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        float val[32], gate[32];
-        tmem_ld32(trow + c, val);
-        tmem_ld32(trow + 64 + c, gate);
-        tmem_ld_wait();
-        epi_chunk32_glu(ep, m, n0 + c, val, gate);
-      }
-    } else {
+    for (int ms = 0; ms < MSUB; ++ms) {
+      const int m = m0 + ms * TC_BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ms * BN;
+      if constexpr (MODE == EPI_GLU) {
+        static_assert(MODE != EPI_GLU || BN % 128 == 0, "GLU pairs live 64 columns apart inside a 128-wide group");
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(trow + c, v);
-        tmem_ld_wait();
-        epi_chunk32<MODE>(ep, m, n0 + c, v);
+        for (int g = 0; g < BN; g += 128) {
+          const int c = g + chalf * 32;
+          float val[32], gate[32];
+          tmem_ld32(trow + c, val);
+          tmem_ld32(trow + c + 64, gate);
+          tmem_ld_wait();
+          epi_chunk32_glu(ep, m, n0 + c, val, gate);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+          float v[32];
+          tmem_ld32(trow + c, v);
+          tmem_ld_wait();
+          epi_chunk32<MODE, TOp>(ep, m, n0 + c, v);
+        }
       }
     }
   }
@@ -279,51 +296,105 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int MODE, int BN>
-static int launch_tc(const float* A, const float* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+template <int MODE, int BN, int MSUB, typename TOp>
+static int launch_tc(const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  using Cfg = TcCfg<BN, MSUB>;
   CUtensorMap tmA, tmB;
-  AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, TC_BM));
-  AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN));
+  AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, TC_BM, (int)sizeof(TOp)));
+  AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, (int)sizeof(TOp)));
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    AVSR_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN, MSUB, TOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmem));
     attr_done = true;
   }
-  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM));
-  gemm_tc_kernel<MODE, BN><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, ep);
+  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM * MSUB));
+  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, ep);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
 
-int gemm_tc(int mode, const float* A, const float* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
-  AVSR_REQUIRE(K >= TC_BK && K % TC_BK == 0, "gemm_tc: K=%d must be a multiple of %d", K, TC_BK);
-  if (M <= 0 || N <= 0) return AVSR_OK;
-  // 128-wide tiles when they already fill the 148 SMs, otherwise 64-wide for more CTAs
-  const bool wide = (long)cdiv(M, TC_BM) * cdiv(N, 128) >= 148;
+// ---------------------------------------------------------------- tile selection
+// Estimated time of one GEMM for tile (MSUB*128) x BN on 148 SMs: the busiest SM's tensor-pipe time vs the bytes
+// every CTA pulls through L2 (operands are re-read once per tile row/column), plus a per-tile epilogue term.
+struct TileChoice { int bn, msub; };
+static const TileChoice kTiles[] = {{64, 1}, {128, 1}, {128, 2}, {256, 1}, {256, 2}};
+
+static TileChoice choose_tile(int mode, int M, int N, int K, int esz) {
+  const double mac_per_cycle = esz == 2 ? 4096.0 : 2048.0;   // per SM, dense f16 / tf32
+  const double l2_bytes_per_cycle = 3400.0;                  // chip-wide L2->SM, measured ~6.6 TB/s at 1.9 GHz
+  double best = 1e30;
+  TileChoice pick = kTiles[0];
+  for (const TileChoice& t : kTiles) {
+    if (mode == EPI_GLU && t.bn % 128 != 0) continue;
+    if (t.bn > 64 && N <= t.bn / 2) continue;                // mostly empty tile
+    const long tiles = (long)cdiv(M, 128 * t.msub) * cdiv(N, t.bn);
+    const long per_sm = (tiles + 147) / 148;
+    const double cta_macs = (double)t.msub * 128.0 * t.bn * K;
+    const double t_mma = per_sm * cta_macs / mac_per_cycle;
+    const double bytes = (double)tiles * ((double)t.msub * 128 + t.bn) * K * esz;
+    const double t_l2 = bytes / l2_bytes_per_cycle;
+    const double t_epi = per_sm * (double)t.msub * t.bn * 6.0 + 2500.0;   // drain + launch/prologue latency
+    const double est = (t_mma > t_l2 ? t_mma : t_l2) + t_epi;
+    if (est < best) { best = est; pick = t; }
+  }
+  return pick;
+}
+
+template <int MODE, typename TOp>
+static int dispatch_tile(TileChoice t, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
+                         cudaStream_t st) {
+  if (t.bn == 64) {
+    if constexpr (MODE != EPI_GLU) return launch_tc<MODE, 64, 1, TOp>(A, Bw, M, N, K, ep, st);
+  }
+  if (t.bn == 128 && t.msub == 1) return launch_tc<MODE, 128, 1, TOp>(A, Bw, M, N, K, ep, st);
+  if (t.bn == 128 && t.msub == 2) return launch_tc<MODE, 128, 2, TOp>(A, Bw, M, N, K, ep, st);
+  if (t.bn == 256 && t.msub == 1) return launch_tc<MODE, 256, 1, TOp>(A, Bw, M, N, K, ep, st);
+  if (t.bn == 256 && t.msub == 2) return launch_tc<MODE, 256, 2, TOp>(A, Bw, M, N, K, ep, st);
+  set_error("gemm_tc: no kernel for tile %dx%d", t.msub * 128, t.bn);
+  return AVSR_E_INVALID;
+}
+
+template <typename TOp>
+static int dispatch_mode(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
+                         cudaStream_t st) {
+  TileChoice t = choose_tile(mode, M, N, K, (int)sizeof(TOp));
+  if (const char* force = getenv("AVSR_B200_TILE")) {        // "BN,MSUB" -- tuning / profiling aid
+    int bn = 0, ms = 0;
+    if (sscanf(force, "%d,%d", &bn, &ms) == 2 && (mode != EPI_GLU || bn % 128 == 0)) t = TileChoice{bn, ms};
+  }
   switch (mode) {
-    case EPI_LINEAR:
-      return wide ? launch_tc<EPI_LINEAR, 128>(A, Bw, M, N, K, ep, st) : launch_tc<EPI_LINEAR, 64>(A, Bw, M, N, K, ep, st);
+    case EPI_LINEAR: return dispatch_tile<EPI_LINEAR, TOp>(t, A, Bw, M, N, K, ep, st);
     case EPI_QK:
       AVSR_REQUIRE(N % 128 == 0, "gemm_tc: QK needs N %% 128 == 0 (N=%d)", N);
-      return wide ? launch_tc<EPI_QK, 128>(A, Bw, M, N, K, ep, st) : launch_tc<EPI_QK, 64>(A, Bw, M, N, K, ep, st);
+      return dispatch_tile<EPI_QK, TOp>(t, A, Bw, M, N, K, ep, st);
     case EPI_VT:
       AVSR_REQUIRE(M % 64 == 0, "gemm_tc: V^T needs M %% 64 == 0 (M=%d)", M);
-      return wide ? launch_tc<EPI_VT, 128>(A, Bw, M, N, K, ep, st) : launch_tc<EPI_VT, 64>(A, Bw, M, N, K, ep, st);
+      return dispatch_tile<EPI_VT, TOp>(t, A, Bw, M, N, K, ep, st);
     case EPI_GLU:
       AVSR_REQUIRE(N % 128 == 0, "gemm_tc: GLU needs N %% 128 == 0 (N=%d)", N);
-      return launch_tc<EPI_GLU, 128>(A, Bw, M, N, K, ep, st);
+      return dispatch_tile<EPI_GLU, TOp>(t, A, Bw, M, N, K, ep, st);
     case EPI_POS:
       AVSR_REQUIRE(N % 64 == 0, "gemm_tc: POS needs N %% 64 == 0 (N=%d)", N);
-      return wide ? launch_tc<EPI_POS, 128>(A, Bw, M, N, K, ep, st) : launch_tc<EPI_POS, 64>(A, Bw, M, N, K, ep, st);
+      return dispatch_tile<EPI_POS, TOp>(t, A, Bw, M, N, K, ep, st);
     default:
       AVSR_REQUIRE(false, "gemm_tc: bad epilogue mode %d", mode);
   }
   return AVSR_OK;
+}
+
+int gemm_tc(int mode, int opk, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t st) {
+  AVSR_REQUIRE(opk == OP_TF32 || opk == OP_F16, "gemm_tc: operand kind %d", opk);
+  const int ke = opk == OP_F16 ? 64 : 32;
+  AVSR_REQUIRE(K >= ke && K % ke == 0, "gemm_tc: K=%d must be a multiple of %d", K, ke);
+  if (M <= 0 || N <= 0) return AVSR_OK;
+  if (opk == OP_F16) return dispatch_mode<__half>(mode, A, Bw, M, N, K, ep, st);
+  return dispatch_mode<float>(mode, A, Bw, M, N, K, ep, st);
 }
 
 }  // namespace avsr

@@ -92,6 +92,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp16 (or bf16) inputs: K = 16 elements per instruction, twice the rate of kind::tf32
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: lane i of the warp receives row (lane base + i); whole warp.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -125,13 +136,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with IEEE half A/B (format 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 }  // namespace sm100
 
-// host: 2-D fp32 row-major tensor (rows x cols, row stride ld elements) -> TMA map with a (box_rows x 32)-element box,
-// 128B swizzle, zero fill out of bounds.
-int make_tmap_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
-// host: 3-D (planes x rows x 64 cols) fp32 tensor -> box (1 x box_rows x 32)
-int make_tmap_3d(CUtensorMap* map, const float* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld_row,
-                 uint64_t ld_plane, uint32_t box_rows);
+// host: 2-D row-major tensor (rows x cols, row stride ld elements of esz = 4 (fp32) or 2 (fp16) bytes) -> TMA map with a
+// (box_rows x 128-byte) box, 128B swizzle, zero fill out of bounds.
+int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 int esz);
+// host: 3-D (planes x rows x cols) tensor -> box (1 x box_rows x 128 bytes)
+int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t planes, uint64_t rows, uint64_t cols, uint64_t ld_row,
+                 uint64_t ld_plane, uint32_t box_rows, int esz);
 
 }  // namespace avsr

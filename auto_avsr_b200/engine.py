@@ -10,13 +10,13 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import EncoderConfig, LayerParams, LAYER_FIELDS, PREC_FP32, PREC_TF32, check, lib
+from ._cabi import EncoderConfig, LayerParams, LAYER_FIELDS, PREC_F16, PREC_FP32, PREC_TF32, check, lib
 
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16}
 
 
 def default_precision() -> str:
-    return os.environ.get("AVSR_B200_PRECISION", "tf32")
+    return os.environ.get("AVSR_B200_PRECISION", "f16")
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:

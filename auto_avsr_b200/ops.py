@@ -27,7 +27,7 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torc
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-           residual: Optional[torch.Tensor] = None, alpha: float = 1.0, precision: str = "tf32") -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, alpha: float = 1.0, precision: str = "f16") -> torch.Tensor:
     """y = [residual + alpha *] act(x W^T + b);  weight (n, k) or (n, k, 1)."""
     x, weight = _prep(x, "x"), _prep(weight, "weight")
     n, k = weight.size(0), weight.size(1)
@@ -37,14 +37,17 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     bias = None if bias is None else _prep(bias, "bias")
     residual = None if residual is None else _prep(residual, "residual")
     y = torch.empty(*x.shape[:-1], n, dtype=torch.float32, device=x.device)
+    nbytes = int(lib.avsr_linear_workspace_bytes(rows, n, k, PRECISIONS[precision]))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.avsr_linear(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(residual), float(alpha), int(relu),
-                              y.data_ptr(), rows, n, k, PRECISIONS[precision], _stream_handle(x.device)))
+                              y.data_ptr(), rows, n, k, PRECISIONS[precision], ws.data_ptr(), ws.numel(),
+                              _stream_handle(x.device)))
     return y
 
 
 def relpos_attention(q, k, v, p, pos_bias_u, pos_bias_v, lengths: Optional[torch.Tensor], n_heads: int,
-                     precision: str = "tf32") -> torch.Tensor:
+                     precision: str = "f16") -> torch.Tensor:
     """q,k,v (B,T,H*64) projected; p (2T-1,H*64) = linear_pos(pos_emb); lengths int32 (B) or None -> ctx (B,T,H*64)."""
     q, k, v, p = _prep(q, "q"), _prep(k, "k"), _prep(v, "v"), _prep(p, "p")
     u, vb = _prep(pos_bias_u, "pos_bias_u"), _prep(pos_bias_v, "pos_bias_v")
@@ -79,16 +82,16 @@ def dwconv_bn_silu(x, weight, bias, bn_weight, bn_bias, bn_mean, bn_var) -> torc
     return y
 
 
-def pointwise_glu(x, weight, bias, precision: str = "tf32") -> torch.Tensor:
+def pointwise_glu(x, weight, bias, precision: str = "f16") -> torch.Tensor:
     """glu(x W^T + b, dim=-1) with W (2C, C[,1]) -> (…, C)   (conformer_encoder.py:32)."""
     x, weight, bias = _prep(x, "x"), _prep(weight, "weight"), _prep(bias, "bias")
     Cc = weight.size(1)
     rows = x.numel() // max(Cc, 1)
     y = torch.empty_like(x)
-    ws = torch.empty(2 * Cc * Cc + 2 * Cc, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.avsr_pointwise_glu_workspace_bytes(rows, Cc)), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.avsr_pointwise_glu(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), rows, Cc,
-                                     ws.data_ptr(), ws.numel() * 4, PRECISIONS[precision], _stream_handle(x.device)))
+                                     ws.data_ptr(), ws.numel(), PRECISIONS[precision], _stream_handle(x.device)))
     return y
 
 

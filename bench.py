@@ -186,24 +186,34 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def kernel_roofline(dev, peaks, precision):
-    """Dominant kernel = the tcgen05 TF32 GEMM (96% of the forward's FLOPs).  Times its largest instance, the FFN
-    w_1 projection (1600 x 3072 x 768, 24 launches per forward), over 24 distinct weight matrices back to back
-    with CUDA events on the launch stream; achieved = algorithmic 2*M*N*K per launch / mean launch duration."""
-    from auto_avsr_b200 import ops
+    """Dominant kernel = the tcgen05 GEMM (92% of the forward's algorithmic FLOPs).  Times its largest instance, the
+    FFN w_1 projection (1600 x 3072 x 768, bias+ReLU epilogue, operand-typed output; 24 launches per forward), over
+    24 distinct weight matrices back to back with CUDA events on the launch stream, operands already in operand
+    storage exactly as inside the encoder; achieved = algorithmic 2*M*N*K per launch / mean launch duration."""
+    import ctypes as C
+    from auto_avsr_b200 import _cabi
+    from auto_avsr_b200.engine import PRECISIONS
     M, N, K = 1600, 3072, 768
+    tdt = torch.float16 if precision == "f16" else torch.float32
     g = torch.Generator().manual_seed(7)
-    x = torch.randn(M, K, generator=g).to(dev)
-    ws = [(torch.rand(N, K, generator=g) - 0.5).to(dev) for _ in range(24)]
+    x = torch.randn(M, K, generator=g).to(dev).to(tdt)
+    ws = [((torch.rand(N, K, generator=g) - 0.5) * 0.07).to(dev).to(tdt) for _ in range(24)]
     b = torch.zeros(N, device=dev)
+    y = torch.empty(M, N, device=dev, dtype=tdt)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def launch(w):
+        _cabi.check(_cabi.lib.avsr_linear_operands(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 1,
+                                                   PRECISIONS[precision], st))
     for w in ws[:3]:
-        ops.linear(x, w, b, relu=True, precision=precision)
+        launch(w)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 4
     e0.record()
     for _ in range(reps):
         for w in ws:
-            ops.linear(x, w, b, relu=True, precision=precision)
+            launch(w)
     e1.record()
     torch.cuda.synchronize(dev)
     per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * len(ws))
@@ -217,11 +227,14 @@ def kernel_roofline(dev, peaks, precision):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<EPI_LINEAR,128> FFN w_1 1600x3072x768 (tcgen05 kind::tf32)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks['source']}); kind::tf32 nominal peak is 0.5x bf16",
-            "frac_of_tf32_nominal": achieved / (0.5 * peak), "us_per_launch": per_launch_s * 1e6,
-            "algorithmic_flops_per_launch": flops, "traffic": traffic}
+    kind = "kind::f16, fp16 operands" if precision == "f16" else "kind::tf32"
+    out = {"bound": "tensor", "kernel": f"gemm_tc_kernel<EPI_LINEAR> FFN w_1 1600x3072x768 (tcgen05 {kind}, fp32 accumulate)",
+           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+           "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks['source']}, cuBLAS bf16 8192^3 burst)",
+           "us_per_launch": per_launch_s * 1e6, "algorithmic_flops_per_launch": flops, "traffic": traffic}
+    if precision == "tf32":
+        out["frac_of_tf32_nominal"] = achieved / (0.5 * peak)
+    return out
 
 
 def run_ours(args):
@@ -309,7 +322,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"f16": "f16 operands, f32 accumulate (f32 residual/LN/softmax)", "tf32": "tf32 operands, f32 accumulate",
+                      "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{WORKLOAD}: lengths={lengths} (max-frames=1600 per GPU), d=768 H=12 ff=3072 L=12 k=31, "
                                    "eval forward, BASELINE.json configs[1]",
                        "global_frames_per_step": sum(lengths) * world, "parallelism": f"dp{world} (one bucket per GPU, "
@@ -325,7 +339,7 @@ def run_ours(args):
                               "frac_of_bf16_peak": algorithmic_flops(lengths) / (ms_max / args.steps * 1e-3) / 1e12
                               / peaks["bf16_tflops"]},
         }
-        if args.precision == "tf32":
+        if args.precision != "fp32":
             line["roofline"] = kernel_roofline(dev, peaks, args.precision)
             log("kernel roofline done")
         if world == 1 and not args.no_cpu:
@@ -347,7 +361,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AVSR_B200_PRECISION", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("AVSR_B200_PRECISION", "f16"),
+                    choices=["f16", "tf32", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

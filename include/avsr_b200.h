@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 1
+#define AVSR_ABI_VERSION 2
 
 enum {
   AVSR_OK = 0,
@@ -39,7 +39,10 @@ enum {
 /* Arithmetic of the GEMM / attention contractions. */
 enum {
   AVSR_PREC_FP32 = 0,  /* CUDA-core fp32 FMA kernels: the on-device exact reference path (slow) */
-  AVSR_PREC_TF32 = 1   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate (the product path) */
+  AVSR_PREC_TF32 = 1,  /* tcgen05 kind::tf32: operands kept as fp32 rounded to TF32, fp32 accumulate */
+  AVSR_PREC_F16 = 2    /* tcgen05 kind::f16: operands stored as IEEE half (same 10-bit mantissa as TF32, saturating
+                          conversion), fp32 accumulate; residual stream, LayerNorm, softmax, conv stay fp32.
+                          Half the operand bytes and twice the MMA rate of TF32: the product path. */
 };
 
 /* Hyper-parameters hard-wired in E2E.__init__ (espnet/nets/pytorch_backend/e2e_asr_conformer.py:33-39):
@@ -81,8 +84,7 @@ uint64_t avsr_launch_count(void);
  * of this implementation: QK weights concatenated, pointwise_cov1 rows interleaved so a GEMM tile
  * holds GLU value+gate pairs, depthwise taps transposed to (K, C), BatchNorm running statistics
  * (conformer_encoder.py:26, eval mode) folded into scale/shift, linear_pos of all layers stacked, and --
- * for AVSR_PREC_TF32 -- GEMM weights rounded to TF32 (round-to-nearest) so the tensor core's operand
- * truncation is exact.  `layers` is a HOST array of num_blocks structs holding DEVICE pointers.
+ * GEMM weights converted to the precision's operand storage (TF32-rounded fp32, or fp16).  `layers` is a HOST array of num_blocks structs holding DEVICE pointers.
  * Must be re-run after the parameters change. */
 size_t avsr_prepared_bytes(const AvsrEncoderConfig *cfg);
 int avsr_prepare_weights(const AvsrEncoderConfig *cfg, const AvsrLayerParams *layers,
@@ -126,9 +128,18 @@ int avsr_layernorm(const float *x, const float *gamma, const float *beta, float 
 
 /* torch.nn.Linear: y = x W^T + b, optionally ReLU (positionwise_feed_forward.py:30) and/or
  * y = resid + alpha*y (conformer_encoder.py:115,140,150,158).  x (rows,k); w (n,k); bias (n) or NULL;
- * resid (rows,n) or NULL (may alias y). */
+ * resid (rows,n) or NULL (may alias y).  All tensors fp32; for AVSR_PREC_F16 x and w are first converted to
+ * half into `workspace` (>= avsr_linear_workspace_bytes), for AVSR_PREC_TF32 the tensor core truncates them. */
+size_t avsr_linear_workspace_bytes(int rows, int n, int k, int precision);
 int avsr_linear(const float *x, const float *w, const float *bias, const float *resid, float alpha,
-                int relu, float *y, int rows, int n, int k, int precision, void *stream);
+                int relu, float *y, int rows, int n, int k, int precision, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* The FFN w_1 GEMM exactly as the encoder runs it: operands ALREADY in `precision`'s operand storage (fp32 for
+ * FP32/TF32, IEEE half for F16), y = relu(x W^T + b) stored as an operand too.  Used by bench.py to time the
+ * dominant kernel in isolation (roofline), not by the modules. */
+int avsr_linear_operands(const void *x_op, const void *w_op, const float *bias, void *y_op, int rows, int n,
+                         int k, int relu, int precision, void *stream);
 
 /* RelPositionMultiHeadedAttention core (transformer/attention.py:174-189 + :59-82), d_k = 64:
  *   scores[b,h,i,j] = ((q_i+u_h).k_j + (q_i+v_h).p_h[rel=i-j]) / 8, key mask j >= lengths[b],
@@ -149,7 +160,8 @@ int avsr_dwconv_bn_silu(const float *x, const float *w, const float *b, const fl
                         int T, int C, int K, void *workspace, size_t workspace_bytes, void *stream);
 
 /* pointwise_cov1 + GLU (conformer_encoder.py:32): y = glu(x W^T + b) over channels, W (2C, C[,1]), b (2C),
- * x (rows, C) -> y (rows, C).  workspace >= (2C*C + 2C) floats (interleaved copy of W, b). */
+ * x (rows, C) -> y (rows, C).  workspace >= avsr_pointwise_glu_workspace_bytes (interleaved W, b; converted x). */
+size_t avsr_pointwise_glu_workspace_bytes(int rows, int C);
 int avsr_pointwise_glu(const float *x, const float *w, const float *b, float *y, int rows, int C,
                        void *workspace, size_t workspace_bytes, int precision, void *stream);
 

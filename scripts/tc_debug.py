@@ -14,6 +14,8 @@ CASES = {
     "linear_mtail": "linear(200, 128, 128)",
     "linear_ffn1": "linear(1600, 3072, 768)",
     "linear_ffn2": "linear(1600, 768, 3072)",
+    "linear_qk": "linear(1600, 1536, 768)",
+    "linear_out": "linear(1600, 768, 768)",
     "attn_small": "attn(1, 64, 1, None)",
     "attn_130": "attn(1, 130, 2, None)",
     "attn_masked": "attn(2, 200, 2, [200, 77])",
@@ -26,6 +28,8 @@ sys.path.insert(0, %(root)r)
 from auto_avsr_b200 import ops
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
+import os
+PREC = os.environ.get("TC_PREC", "f16")
 
 def report(name, y, ref):
     d = (y.double() - ref.double()).abs()
@@ -46,7 +50,7 @@ def report(name, y, ref):
 def linear(M, N, K):
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / math.sqrt(K); b = torch.randn(N, device=dev)
     ref = ops.linear(x, w, b, precision="fp32")
-    y = ops.linear(x, w, b, precision="tf32")
+    y = ops.linear(x, w, b, precision=PREC)
     torch.cuda.synchronize()
     report(f"linear {M}x{N}x{K}", y, ref)
 
@@ -57,7 +61,7 @@ def attn(B, T, H, lengths):
     u, vb = torch.randn(H, 64, device=dev) * 0.3, torch.randn(H, 64, device=dev) * 0.3
     ln = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=dev)
     ref = ops.relpos_attention(q, k, v, p, u, vb, ln, H, precision="fp32")
-    y = ops.relpos_attention(q, k, v, p, u, vb, ln, H, precision="tf32")
+    y = ops.relpos_attention(q, k, v, p, u, vb, ln, H, precision=PREC)
     torch.cuda.synchronize()
     report(f"attn B{B} T{T} H{H} {lengths}", y.view(B * T, D), ref.view(B * T, D))
 
