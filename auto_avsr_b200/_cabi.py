@@ -70,7 +70,7 @@ SIGNATURES = {
     "avsr_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "avsr_linear_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "avsr_linear": (_I, [_P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _P, _Z, _P]),
-    "avsr_linear_operands": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "avsr_linear_operands": (_I, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _P]),
     "avsr_attention_workspace_bytes": (_Z, [_I, _I, _I]),
     "avsr_relpos_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
     "avsr_dwconv_bn_silu": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),

@@ -486,12 +486,12 @@ int avsr_linear(const float* x, const float* w, const float* bias, const float* 
   return run_gemm(precision, EPI_LINEAR, xa, wa, rows, n, k, epi_linear(rows, n, bias, y, resid, alpha, relu, 0), st);
 }
 
-int avsr_linear_operands(const void* x_op, const void* w_op, const float* bias, void* y_op, int rows, int n, int k,
-                         int relu, int precision, void* stream) {
-  AVSR_REQUIRE(x_op && w_op && y_op, "NULL argument");
+int avsr_linear_operands(const void* x_op, const void* w_op, const float* bias, const float* resid, float alpha,
+                         void* y, int rows, int n, int k, int relu, int y_is_operand, int precision, void* stream) {
+  AVSR_REQUIRE(x_op && w_op && y, "NULL argument");
   AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   return run_gemm(precision, EPI_LINEAR, x_op, w_op, rows, n, k,
-                  epi_linear(rows, n, bias, reinterpret_cast<float*>(y_op), nullptr, 0.f, relu, precision != AVSR_PREC_FP32),
+                  epi_linear(rows, n, bias, y, resid, alpha, relu, (y_is_operand && precision != AVSR_PREC_FP32) ? 1 : 0),
                   reinterpret_cast<cudaStream_t>(stream));
 }
 

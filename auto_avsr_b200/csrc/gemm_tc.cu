@@ -73,92 +73,114 @@ int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t planes, uint64_t r
   return AVSR_OK;
 }
 
-// ---------------------------------------------------------------- vectorised epilogues: one row, 32 columns
-// `v` holds acc[m][n .. n+31]; n is a multiple of 32.  TOp is the storage type of operand-typed destinations.
-template <int MODE, typename TOp>
-__device__ __forceinline__ void epi_chunk32(const EpiParams& p, int m, int n, const float* v) {
-  if (m >= p.M || n >= p.N) return;
-  if constexpr (MODE == EPI_LINEAR) {
-    if (n + 32 <= p.N && (p.ldo & 3) == 0) {
-      const long off = (long)m * p.ldo + n;
-      const float* res = p.resid ? p.resid + off : nullptr;
+// ---------------------------------------------------------------- staged (coalesced) epilogue
+// Each epilogue warp drains 32 accumulator rows x CW columns at a time: lane = row out of TMEM (tcgen05.ld), per-
+// column math (bias / ReLU / GLU / pos biases, vectors read from shared memory), conversion to the destination
+// storage, then a transpose through a private 32 x 144-byte staging buffer (carved from the pipeline stages, which
+// are idle once the accumulator is complete) so that global memory sees, per quarter-warp, 8 lanes x 16 B = one full
+// 128-byte row segment -- instead of 32 partial sectors per store instruction (r01 profile: the direct
+// lane-per-row stores made the epilogue 4x longer than the MMA main loop).  Residual reads use the same mapping.
+constexpr int STG_ROW = 144;            // 128 B payload + 16 B pad: conflict-free lane-per-row 16-byte writes
+constexpr int STG_WARP = 32 * STG_ROW;  // 4608 B per epilogue warp
+
+// lane writes its row: 32 fp32 values, optionally rounded to TF32
+__device__ __forceinline__ void stage_write_f32(uint8_t* stg, int lane, const float* o, bool round) {
+  uint8_t* row = stg + lane * STG_ROW;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (p.bias) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + n + j);
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-        }
-        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (res) {
-          const float4 r = *reinterpret_cast<const float4*>(res + j);
-          o.x = r.x + p.alpha * o.x; o.y = r.y + p.alpha * o.y; o.z = r.z + p.alpha * o.z; o.w = r.w + p.alpha * o.w;
-        }
-        if (p.round_out) store_op4<TOp>(reinterpret_cast<TOp*>(p.out) + off + j, o.x, o.y, o.z, o.w);
-        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = o;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) epi_store<EPI_LINEAR, TOp>(p, m, n + j, v[j]);
-    }
-  } else if constexpr (MODE == EPI_QK) {
-    const int D = p.H * kHeadDim;                 // multiple of 64, so a 32-chunk never straddles q|k or a head
-    const int b = m / p.T, t = m - b * p.T;
-    const int nn = n < D ? n : n - D;
-    const int h = nn / kHeadDim, d0 = nn - h * kHeadDim;
-    const long idx = (((long)b * p.H + h) * p.T + t) * kHeadDim + d0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 bq = *reinterpret_cast<const float4*>(p.bias + n + j);
-      const float4 o = make_float4(v[j] + bq.x, v[j + 1] + bq.y, v[j + 2] + bq.z, v[j + 3] + bq.w);
-      if (n < D) {
-        const float4 u = *reinterpret_cast<const float4*>(p.pos_u + nn + j);
-        const float4 w = *reinterpret_cast<const float4*>(p.pos_v + nn + j);
-        store_op4<TOp>(reinterpret_cast<TOp*>(p.qu) + idx + j, o.x + u.x, o.y + u.y, o.z + u.z, o.w + u.w);
-        store_op4<TOp>(reinterpret_cast<TOp*>(p.qv) + idx + j, o.x + w.x, o.y + w.y, o.z + w.z, o.w + w.w);
-      } else {
-        store_op4<TOp>(reinterpret_cast<TOp*>(p.kk) + idx + j, o.x, o.y, o.z, o.w);
-      }
-    }
-  } else if constexpr (MODE == EPI_VT) {
-    // m = v feature (h*64+d), n.. = 32 consecutive frames: contiguous in v^T unless an utterance boundary intervenes
-    const int h = m / kHeadDim, d = m - h * kHeadDim;
-    const float bias = p.bias[m];
-    const int b0 = n / p.T, t0 = n - b0 * p.T;
-    if (t0 + 32 <= p.T && n + 32 <= p.N && (t0 & 3) == 0) {
-      TOp* dst = reinterpret_cast<TOp*>(p.vt) + (((long)b0 * p.H + h) * kHeadDim + d) * p.Tp + t0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) store_op4<TOp>(dst + j, v[j] + bias, v[j + 1] + bias, v[j + 2] + bias, v[j + 3] + bias);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) epi_store<EPI_VT, TOp>(p, m, n + j, v[j]);
-    }
-  } else if constexpr (MODE == EPI_POS) {
-    const int D = p.H * kHeadDim;
-    const int l = n / D, r = n - l * D;
-    const int h = r / kHeadDim, d0 = r - h * kHeadDim;
-    TOp* dst = reinterpret_cast<TOp*>(p.out) + (((long)l * p.H + h) * p.Rp + m) * kHeadDim + d0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) store_op4<TOp>(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int j = 0; j < 8; ++j) {
+    float4 t = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    if (round) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+    *reinterpret_cast<float4*>(row + 16 * j) = t;
   }
 }
-
-// GLU: value columns n .. n+31 (n % 128 < 64), gates 64 columns further; out column = (n/128)*64 + n%128 (fp32)
-__device__ __forceinline__ void epi_chunk32_glu(const EpiParams& p, int m, int n, const float* val, const float* gate) {
-  if (m >= p.M || n + 64 >= p.N) return;
-  const int c0 = (n >> 7) * 64 + (n & 127);
-  float* dst = reinterpret_cast<float*>(p.out) + (long)m * p.ldo + c0;
+// lane writes its row: 64 values converted to half (128 bytes)
+__device__ __forceinline__ void stage_write_f16(uint8_t* stg, int lane, const float* o) {
+  uint8_t* row = stg + lane * STG_ROW;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 ba = *reinterpret_cast<const float4*>(p.bias + n + j);
-    const float4 bg = *reinterpret_cast<const float4*>(p.bias + n + 64 + j);
-    float4 o;
-    o.x = (val[j] + ba.x) * sigmoidf_acc(gate[j] + bg.x);
-    o.y = (val[j + 1] + ba.y) * sigmoidf_acc(gate[j + 1] + bg.y);
-    o.z = (val[j + 2] + ba.z) * sigmoidf_acc(gate[j + 2] + bg.z);
-    o.w = (val[j + 3] + ba.w) * sigmoidf_acc(gate[j + 3] + bg.w);
-    *reinterpret_cast<float4*>(dst + j) = o;
+  for (int j = 0; j < 8; ++j) {
+    uint4 t;
+    __half2 h0 = __halves2half2(to_half_sat(o[8 * j]), to_half_sat(o[8 * j + 1]));
+    __half2 h1 = __halves2half2(to_half_sat(o[8 * j + 2]), to_half_sat(o[8 * j + 3]));
+    __half2 h2 = __halves2half2(to_half_sat(o[8 * j + 4]), to_half_sat(o[8 * j + 5]));
+    __half2 h3 = __halves2half2(to_half_sat(o[8 * j + 6]), to_half_sat(o[8 * j + 7]));
+    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(row + 16 * j) = t;
   }
+}
+template <typename TOp> struct StageOp;
+template <> struct StageOp<float> {
+  static constexpr int kCols = 32;   // operand columns per 128-byte row segment
+  __device__ static void write(uint8_t* stg, int lane, const float* o) { stage_write_f32(stg, lane, o, true); }
+};
+template <> struct StageOp<__half> {
+  static constexpr int kCols = 64;
+  __device__ static void write(uint8_t* stg, int lane, const float* o) { stage_write_f16(stg, lane, o); }
+};
+// transposed read: iteration `it` (0..7) gives this lane the 16-byte piece (lane & 7) of row it*4 + (lane >> 3)
+__device__ __forceinline__ uint4 stage_read(const uint8_t* stg, int it, int lane) {
+  return *reinterpret_cast<const uint4*>(stg + (it * 4 + (lane >> 3)) * STG_ROW + (lane & 7) * 16);
+}
+
+// ---- per-mode emit of one 16-byte piece: row m, first column n (global indices of the GEMM) ----
+// fp32 destination (LINEAR): y = [resid + alpha *] val
+__device__ __forceinline__ void emit_linear_f32(const EpiParams& p, int m, int n, uint4 pay) {
+  if (m >= p.M || n >= p.N) return;
+  const long off = (long)m * p.ldo + n;
+  float4 v = *reinterpret_cast<float4*>(&pay);
+  if (p.resid) {
+    const float4 r = *reinterpret_cast<const float4*>(p.resid + off);
+    v.x = r.x + p.alpha * v.x; v.y = r.y + p.alpha * v.y; v.z = r.z + p.alpha * v.z; v.w = r.w + p.alpha * v.w;
+  }
+  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
+}
+template <typename TOp>
+__device__ __forceinline__ void emit_linear_op(const EpiParams& p, int m, int n, uint4 pay) {
+  if (m >= p.M || n >= p.N) return;
+  *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(p.out) + (long)m * p.ldo + n) = pay;
+}
+template <typename TOp>
+__device__ __forceinline__ void emit_heads(const EpiParams& p, void* base, int m, int n, uint4 pay) {  // QK
+  if (m >= p.M || n >= p.N) return;
+  const int D = p.H * kHeadDim;
+  const int b = m / p.T, t = m - b * p.T;
+  const int nn = n < D ? n : n - D;
+  const int h = nn >> 6, d0 = nn & 63;
+  *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(base) + (((long)b * p.H + h) * p.T + t) * kHeadDim + d0) = pay;
+}
+template <typename TOp>
+__device__ __forceinline__ void emit_vt(const EpiParams& p, int m, int n, uint4 pay) {  // m = feature, n = frame
+  constexpr int NE = 16 / (int)sizeof(TOp);
+  if (m >= p.M || n >= p.N) return;
+  const int h = m >> 6, d = m & 63;
+  const int b0 = n / p.T, t0 = n - b0 * p.T;
+  TOp* vt = reinterpret_cast<TOp*>(p.vt);
+  if (t0 + NE <= p.T && n + NE <= p.N && (t0 % NE) == 0) {
+    *reinterpret_cast<uint4*>(vt + (((long)b0 * p.H + h) * kHeadDim + d) * p.Tp + t0) = pay;
+  } else {   // utterance boundary / ragged T: element-wise
+    const TOp* e = reinterpret_cast<const TOp*>(&pay);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int ne = n + i;
+      if (ne < p.N) {
+        const int b = ne / p.T, t = ne - b * p.T;
+        vt[(((long)b * p.H + h) * kHeadDim + d) * p.Tp + t] = e[i];
+      }
+    }
+  }
+}
+template <typename TOp>
+__device__ __forceinline__ void emit_pos(const EpiParams& p, int m, int n, uint4 pay) {
+  if (m >= p.M || n >= p.N) return;
+  const int D = p.H * kHeadDim;
+  const int l = n / D, r = n - l * D;
+  const int h = r >> 6, d0 = r & 63;
+  *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(p.out) + (((long)l * p.H + h) * p.Rp + m) * kHeadDim + d0) = pay;
+}
+__device__ __forceinline__ void emit_glu(const EpiParams& p, int m, int n_val, uint4 pay) {  // fp32 dest
+  if (m >= p.M || n_val + 64 >= p.N) return;
+  const int c = (n_val >> 7) * 64 + (n_val & 127);
+  *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + (long)m * p.ldo + c) = pay;
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -172,10 +194,11 @@ struct TcCfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kCtasPerSm = (MSUB == 1 && BN <= 128) ? 2 : 1;
-  static constexpr int kStagesFit = (TC_SMEM_BUDGET / kCtasPerSm) / kStageBytes;
+  static constexpr int kStagesFit = (TC_SMEM_BUDGET / kCtasPerSm - 4096) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kTmemCols = MSUB * BN;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kVecBytes = 3 * BN * 4;   // bias / pos_bias_u / pos_bias_v of the tile's columns
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kVecBytes;
   static_assert(kStages >= 2, "tile too large for shared memory");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
@@ -205,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* gen = tc_smem_raw + (base - raw);
   const uint32_t bars = base + S * Cfg::kStageBytes;  // full[S], empty[S], tmem_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * Cfg::kStageBytes + (2 * S + 1) * 8);
+  float* s_vec = reinterpret_cast<float*>(gen + S * Cfg::kStageBytes + 256);   // [3][BN]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * S);
@@ -264,11 +288,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp drains
+    // stage the tile's per-column vectors in shared memory while the mainloop runs
+    {
+      float* s_bias = s_vec;
+      float* s_u = s_vec + BN;
+      float* s_v = s_vec + 2 * BN;
+      const int D = ep.H * kHeadDim;
+      for (int c = threadIdx.x - 64; c < BN; c += TC_THREADS - 64) {
+        const int n = n0 + c;
+        float bv = 0.f, uv = 0.f, vv = 0.f;
+        if constexpr (MODE != EPI_VT && MODE != EPI_POS) {
+          if (ep.bias && n < ep.N) bv = ep.bias[n];
+        }
+        if constexpr (MODE == EPI_QK) {
+          if (n < D) { uv = ep.pos_u[n]; vv = ep.pos_v[n]; }
+        }
+        s_bias[c] = bv; s_u[c] = uv; s_v[c] = vv;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // every TMA write has landed and every MMA has read its operands: the pipeline stages are free -> staging
+    uint8_t* stg = gen + (warp - 2) * STG_WARP;
+    const int cb = chalf * (BN / 2), ce = cb + BN / 2;      // this warp's columns of the tile
+    const int pr = lane >> 3;                                // row (of 4) this lane emits per read iteration
+    const int pc = lane & 7;                                 // 16-byte piece of the 128-byte row segment
+    constexpr int OC = StageOp<TOp>::kCols;                  // operand columns per row segment (32 tf32 / 64 f16)
+    constexpr int ONE = 16 / (int)sizeof(TOp);               // operand elements per 16-byte piece
 #pragma unroll 1
     for (int ms = 0; ms < MSUB; ++ms) {
-      const int m = m0 + ms * TC_BM + q * 32 + lane;
+      const int mw = m0 + ms * TC_BM + q * 32;               // first row of this warp's 32-row slab
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ms * BN;
       if constexpr (MODE == EPI_GLU) {
         static_assert(MODE != EPI_GLU || BN % 128 == 0, "GLU pairs live 64 columns apart inside a 128-wide group");
@@ -279,15 +329,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(trow + c, val);
           tmem_ld32(trow + c + 64, gate);
           tmem_ld_wait();
-          epi_chunk32_glu(ep, m, n0 + c, val, gate);
+          const float* sb = s_vec + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = (val[j] + sb[j]) * sigmoidf_acc(gate[j] + sb[64 + j]);
+          stage_write_f32(stg, lane, val, false);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) emit_glu(ep, mw + it * 4 + pr, n0 + c + pc * 4, stage_read(stg, it, lane));
+          __syncwarp();
+        }
+      } else if constexpr (MODE == EPI_LINEAR) {
+        if (!ep.round_out) {                                 // fp32 destination (+ residual)
+#pragma unroll 1
+          for (int c = cb; c < ce; c += 32) {
+            float v[32];
+            tmem_ld32(trow + c, v);
+            tmem_ld_wait();
+            const float* sb = s_vec + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+            stage_write_f32(stg, lane, v, false);
+            __syncwarp();
+            // residual pieces first (8 independent coalesced loads in flight), then combine + store: a load may not
+            // be hoisted above a store by the compiler (possible aliasing), so the order is made explicit here
+            const int n = n0 + c + pc * 4;
+            float4 r[8];
+            if (ep.resid) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int m = mw + it * 4 + pr;
+                r[it] = (m < ep.M && n < ep.N) ? *reinterpret_cast<const float4*>(ep.resid + (long)m * ep.ldo + n)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int m = mw + it * 4 + pr;
+              const uint4 pay = stage_read(stg, it, lane);
+              float4 o = *reinterpret_cast<const float4*>(&pay);
+              if (ep.resid) {
+                o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
+                o.z = r[it].z + ep.alpha * o.z; o.w = r[it].w + ep.alpha * o.w;
+              }
+              if (m < ep.M && n < ep.N)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long)m * ep.ldo + n) = o;
+            }
+            __syncwarp();
+          }
+        } else {                                             // operand-typed destination (FFN hidden)
+#pragma unroll 1
+          for (int c = cb; c < ce; c += OC) {
+            float v[OC];
+#pragma unroll
+            for (int k = 0; k < OC; k += 32) tmem_ld32(trow + c + k, v + k);
+            tmem_ld_wait();
+            const float* sb = s_vec + c;
+#pragma unroll
+            for (int j = 0; j < OC; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+            StageOp<TOp>::write(stg, lane, v);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              emit_linear_op<TOp>(ep, mw + it * 4 + pr, n0 + c + pc * ONE, stage_read(stg, it, lane));
+            __syncwarp();
+          }
         }
       } else {
+        float row_bias = 0.f;                                // V^T: the bias is per output ROW (feature)
+        if constexpr (MODE == EPI_VT) { const int m = mw + lane; row_bias = (m < ep.M) ? ep.bias[m] : 0.f; }
+        const int D = ep.H * kHeadDim;
 #pragma unroll 1
-        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-          float v[32];
-          tmem_ld32(trow + c, v);
+        for (int c = cb; c < ce; c += OC) {
+          float v[OC];
+#pragma unroll
+          for (int k = 0; k < OC; k += 32) tmem_ld32(trow + c + k, v + k);
           tmem_ld_wait();
-          epi_chunk32<MODE, TOp>(ep, m, n0 + c, v);
+          const int n = n0 + c;
+          if constexpr (MODE == EPI_QK) {
+            const float* sb = s_vec + c;
+#pragma unroll
+            for (int j = 0; j < OC; ++j) v[j] += sb[j];
+            if (n < D) {                                     // q: two outputs, q + pos_bias_u and q + pos_bias_v
+              const float* su = s_vec + BN + c;
+#pragma unroll
+              for (int j = 0; j < OC; ++j) v[j] += su[j];
+              StageOp<TOp>::write(stg, lane, v);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                emit_heads<TOp>(ep, ep.qu, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+              __syncwarp();
+              // second output: re-read the accumulator chunk (cheaper than keeping two register copies)
+#pragma unroll
+              for (int k = 0; k < OC; k += 32) tmem_ld32(trow + c + k, v + k);
+              tmem_ld_wait();
+              const float* sv = s_vec + 2 * BN + c;
+#pragma unroll
+              for (int j = 0; j < OC; ++j) v[j] += sb[j] + sv[j];
+              StageOp<TOp>::write(stg, lane, v);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                emit_heads<TOp>(ep, ep.qv, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+              __syncwarp();
+            } else {
+              StageOp<TOp>::write(stg, lane, v);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                emit_heads<TOp>(ep, ep.kk, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+              __syncwarp();
+            }
+          } else {
+            if constexpr (MODE == EPI_VT) {
+#pragma unroll
+              for (int j = 0; j < OC; ++j) v[j] += row_bias;
+            }
+            StageOp<TOp>::write(stg, lane, v);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const uint4 pay = stage_read(stg, it, lane);
+              if constexpr (MODE == EPI_VT) emit_vt<TOp>(ep, mw + it * 4 + pr, n + pc * ONE, pay);
+              else emit_pos<TOp>(ep, mw + it * 4 + pr, n + pc * ONE, pay);
+            }
+            __syncwarp();
+          }
         }
       }
     }
@@ -324,13 +491,14 @@ static int launch_tc(const void* A, const void* Bw, int M, int N, int K, const E
 struct TileChoice { int bn, msub; };
 static const TileChoice kTiles[] = {{64, 1}, {128, 1}, {128, 2}, {256, 1}, {256, 2}};
 
-static TileChoice choose_tile(int mode, int M, int N, int K, int esz) {
+static TileChoice choose_tile(int mode, int M, int N, int K, int esz, bool operand_dest) {
   const double mac_per_cycle = esz == 2 ? 4096.0 : 2048.0;   // per SM, dense f16 / tf32
-  const double l2_bytes_per_cycle = 3400.0;                  // chip-wide L2->SM, measured ~6.6 TB/s at 1.9 GHz
+  const double l2_bytes_per_cycle = 6000.0;                  // chip-wide L2->SM bytes per SM-clock (>= 11 TB/s observed)
   double best = 1e30;
   TileChoice pick = kTiles[0];
   for (const TileChoice& t : kTiles) {
     if (mode == EPI_GLU && t.bn % 128 != 0) continue;
+    if (t.bn == 64 && esz == 2 && (mode != EPI_LINEAR || operand_dest)) continue;   // needs 64-column row segments
     if (t.bn > 64 && N <= t.bn / 2) continue;                // mostly empty tile
     const long tiles = (long)cdiv(M, 128 * t.msub) * cdiv(N, t.bn);
     const long per_sm = (tiles + 147) / 148;
@@ -362,10 +530,19 @@ static int dispatch_tile(TileChoice t, const void* A, const void* Bw, int M, int
 template <typename TOp>
 static int dispatch_mode(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
                          cudaStream_t st) {
-  TileChoice t = choose_tile(mode, M, N, K, (int)sizeof(TOp));
+  const bool operand_dest = mode != EPI_GLU && (mode != EPI_LINEAR || ep.round_out != 0);
+  TileChoice t = choose_tile(mode, M, N, K, (int)sizeof(TOp), operand_dest);
   if (const char* force = getenv("AVSR_B200_TILE")) {        // "BN,MSUB" -- tuning / profiling aid
     int bn = 0, ms = 0;
-    if (sscanf(force, "%d,%d", &bn, &ms) == 2 && (mode != EPI_GLU || bn % 128 == 0)) t = TileChoice{bn, ms};
+    if (sscanf(force, "%d,%d", &bn, &ms) == 2 && (mode != EPI_GLU || bn % 128 == 0) &&
+        !(bn == 64 && sizeof(TOp) == 2 && operand_dest))
+      t = TileChoice{bn, ms};
+  }
+  AVSR_REQUIRE(mode == EPI_VT || N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", N);
+  if (mode == EPI_LINEAR) {
+    AVSR_REQUIRE((ep.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0,
+                 "gemm_tc: output / residual must be 16-byte aligned with a row stride that is a multiple of 8");
   }
   switch (mode) {
     case EPI_LINEAR: return dispatch_tile<EPI_LINEAR, TOp>(t, A, Bw, M, N, K, ep, st);

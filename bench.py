@@ -203,17 +203,26 @@ def kernel_roofline(dev, peaks, precision):
     st = torch.cuda.current_stream(dev).cuda_stream
 
     def launch(w):
-        _cabi.check(_cabi.lib.avsr_linear_operands(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 1,
-                                                   PRECISIONS[precision], st))
+        nonlocal st
+        _cabi.check(_cabi.lib.avsr_linear_operands(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, 0.0, y.data_ptr(),
+                                                   M, N, K, 1, 1, PRECISIONS[precision], st))
     for w in ws[:3]:
         launch(w)
+    torch.cuda.synchronize(dev)
+    # replay the 24 launches from a CUDA graph (as the encoder does): the python/ctypes launch path (~10 us) would
+    # otherwise be what is timed, not the kernel
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for w in ws:
+            launch(w)
+    graph.replay()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 4
     e0.record()
     for _ in range(reps):
-        for w in ws:
-            launch(w)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize(dev)
     per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * len(ws))

@@ -135,11 +135,12 @@ int avsr_linear(const float *x, const float *w, const float *bias, const float *
                 int relu, float *y, int rows, int n, int k, int precision, void *workspace,
                 size_t workspace_bytes, void *stream);
 
-/* The FFN w_1 GEMM exactly as the encoder runs it: operands ALREADY in `precision`'s operand storage (fp32 for
- * FP32/TF32, IEEE half for F16), y = relu(x W^T + b) stored as an operand too.  Used by bench.py to time the
- * dominant kernel in isolation (roofline), not by the modules. */
-int avsr_linear_operands(const void *x_op, const void *w_op, const float *bias, void *y_op, int rows, int n,
-                         int k, int relu, int precision, void *stream);
+/* A projection GEMM exactly as the encoder runs it: x and w ALREADY in `precision`'s operand storage (fp32 for
+ * FP32/TF32, IEEE half for F16); y = [resid + alpha *] act(x W^T + b), stored as an operand (y_is_operand != 0,
+ * e.g. the FFN hidden) or as fp32 (the residual stream).  Used by bench.py / the tile sweep to time the dominant
+ * kernel in isolation (roofline), not by the modules. */
+int avsr_linear_operands(const void *x_op, const void *w_op, const float *bias, const float *resid, float alpha,
+                         void *y, int rows, int n, int k, int relu, int y_is_operand, int precision, void *stream);
 
 /* RelPositionMultiHeadedAttention core (transformer/attention.py:174-189 + :59-82), d_k = 64:
  *   scores[b,h,i,j] = ((q_i+u_h).k_j + (q_i+v_h).p_h[rel=i-j]) / 8, key mask j >= lengths[b],
