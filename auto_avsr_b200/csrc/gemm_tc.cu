@@ -186,19 +186,21 @@ __device__ __forceinline__ void emit_glu(const EpiParams& p, int m, int n_val, u
 // ---------------------------------------------------------------- the kernel
 constexpr int TC_BM = 128;          // rows per UMMA / per A box
 constexpr int TC_THREADS = 320;     // TMA warp + MMA warp + 8 epilogue warps
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_SMEM_BUDGET = 222 * 1024;   // one persistent CTA per SM
 
 template <int BN, int MSUB>
 struct TcCfg {
   static constexpr int kABytes = MSUB * TC_BM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kCtasPerSm = (MSUB == 1 && BN <= 128) ? 2 : 1;
-  static constexpr int kStagesFit = (TC_SMEM_BUDGET / kCtasPerSm - 4096) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kTmemCols = MSUB * BN;
-  static constexpr int kVecBytes = 3 * BN * 4;   // bias / pos_bias_u / pos_bias_v of the tile's columns
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kVecBytes;
+  static constexpr int kAccStages = (2 * MSUB * BN <= 512) ? 2 : 1;   // double-buffered accumulator when it fits TMEM
+  static constexpr int kTmemCols = kAccStages * MSUB * BN;
+  static constexpr int kVecBytes = 3 * BN * 4;          // bias / pos_bias_u / pos_bias_v of the tile's columns
+  static constexpr int kStagingBytes = 8 * STG_WARP;    // epilogue transpose buffers (dedicated: the ring stays busy)
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + 256 /*barriers*/ + kVecBytes + kStagingBytes;
+  static constexpr int kStagesFit = (TC_SMEM_BUDGET - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmem = kStages * kStageBytes + kFixedBytes;
   static_assert(kStages >= 2, "tile too large for shared memory");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
@@ -216,32 +218,40 @@ template <> struct OpTraits<__half> {
 };
 
 template <int MODE, int BN, int MSUB, typename TOp>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MSUB>::kCtasPerSm)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, EpiParams ep) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_m,
+               int tiles_n, EpiParams ep) {
+  // PERSISTENT: CTA c processes tiles c, c + gridDim.x, ... (n fastest, so concurrently running CTAs share A rows in
+  // L2).  The TMA ring never drains between tiles and the accumulator is double-buffered in TMEM, so the epilogue of
+  // tile i overlaps the main loop of tile i+1 (at K = 768 a tile is only 12 k-blocks: per-tile prologue / pipeline
+  // fill / drain latency was ~3x the tensor-pipe time in the one-tile-per-CTA version, r01 tile sweep).
   using Cfg = TcCfg<BN, MSUB>;
   using Op = OpTraits<TOp>;
   constexpr int S = Cfg::kStages;
+  constexpr int ACC = Cfg::kAccStages;
   constexpr int KE = Op::kElemsPerBlock;
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* gen = tc_smem_raw + (base - raw);
-  const uint32_t bars = base + S * Cfg::kStageBytes;  // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * Cfg::kStageBytes + (2 * S + 1) * 8);
+  const uint32_t bars = base + S * Cfg::kStageBytes;  // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * Cfg::kStageBytes + (2 * S + 4) * 8);
   float* s_vec = reinterpret_cast<float*>(gen + S * Cfg::kStageBytes + 256);   // [3][BN]
+  uint8_t* stg_base = gen + S * Cfg::kStageBytes + 256 + Cfg::kVecBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * S);
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * (TC_BM * MSUB), n0 = blockIdx.x * BN;
   const int nkb = K / KE;
+  const int total_tiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
@@ -252,48 +262,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-        const uint32_t a_dst = base + s * Cfg::kStageBytes;
+      int it = 0;                                       // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * (TC_BM * MSUB), n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const uint32_t a_dst = base + s * Cfg::kStageBytes;
 #pragma unroll
-        for (int ms = 0; ms < MSUB; ++ms)
-          tma_load_2d(a_dst + ms * (TC_BM * 128), &tmA, kb * KE, m0 + ms * TC_BM, full_bar(s));
-        tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * KE, n0, full_bar(s));
+          for (int ms = 0; ms < MSUB; ++ms)
+            tma_load_2d(a_dst + ms * (TC_BM * 128), &tmA, kb * KE, m0 + ms * TC_BM, full_bar(s));
+          tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * KE, n0, full_bar(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = Op::idesc(TC_BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int acc = (ACC == 2) ? (t & 1) : 0;
+        const uint32_t acc_ph = ((ACC == 2) ? (t >> 1) : t) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);     // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = base + s * Cfg::kStageBytes;
-        const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
+        const uint32_t tacc = tmem_base + acc * (MSUB * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = base + s * Cfg::kStageBytes;
+          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
-        for (int ms = 0; ms < MSUB; ++ms) {
-          const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
+          for (int ms = 0; ms < MSUB; ++ms) {
+            const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
-            Op::mma(tmem_base + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
+              Op::mma(tacc + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(empty_bar(s));
         }
-        tc_commit(empty_bar(s));
+        tc_commit(tmem_full_bar(acc));
       }
-      tc_commit(tmem_full_bar);
     }
   } else {
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int chalf = (warp - 2) >> 2;           // which half of the tile's columns this warp drains
-    // stage the tile's per-column vectors in shared memory while the mainloop runs
+    uint8_t* stg = stg_base + (warp - 2) * STG_WARP;
+    const int cb = chalf * (BN / 2), ce = cb + BN / 2;      // this warp's columns of the tile
+    const int pr = lane >> 3;                                // row (of 4) this lane emits per read iteration
+    const int pc = lane & 7;                                 // 16-byte piece of the 128-byte row segment
+    constexpr int OC = StageOp<TOp>::kCols;                  // operand columns per row segment (32 tf32 / 64 f16)
+    constexpr int ONE = 16 / (int)sizeof(TOp);               // operand elements per 16-byte piece
+    int t = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    const int m0 = (tile / tiles_n) * (TC_BM * MSUB), n0 = (tile % tiles_n) * BN;
+    const int acc = (ACC == 2) ? (t & 1) : 0;
+    const uint32_t acc_ph = ((ACC == 2) ? (t >> 1) : t) & 1;
+    // stage the tile's per-column vectors in shared memory (overlaps the main loop of this tile)
     {
       float* s_bias = s_vec;
       float* s_u = s_vec + BN;
       float* s_v = s_vec + 2 * BN;
       const int D = ep.H * kHeadDim;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers of s_vec are done
       for (int c = threadIdx.x - 64; c < BN; c += TC_THREADS - 64) {
         const int n = n0 + c;
         float bv = 0.f, uv = 0.f, vv = 0.f;
@@ -307,19 +342,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
     }
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar(acc), acc_ph);
     tc_fence_after();
-    // every TMA write has landed and every MMA has read its operands: the pipeline stages are free -> staging
-    uint8_t* stg = gen + (warp - 2) * STG_WARP;
-    const int cb = chalf * (BN / 2), ce = cb + BN / 2;      // this warp's columns of the tile
-    const int pr = lane >> 3;                                // row (of 4) this lane emits per read iteration
-    const int pc = lane & 7;                                 // 16-byte piece of the 128-byte row segment
-    constexpr int OC = StageOp<TOp>::kCols;                  // operand columns per row segment (32 tf32 / 64 f16)
-    constexpr int ONE = 16 / (int)sizeof(TOp);               // operand elements per 16-byte piece
+    const uint32_t tacc = tmem_base + acc * (MSUB * BN);
 #pragma unroll 1
     for (int ms = 0; ms < MSUB; ++ms) {
       const int mw = m0 + ms * TC_BM + q * 32;               // first row of this warp's 32-row slab
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ms * BN;
+      const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16) + ms * BN;
       if constexpr (MODE == EPI_GLU) {
         static_assert(MODE != EPI_GLU || BN % 128 == 0, "GLU pairs live 64 columns apart inside a 128-wide group");
 #pragma unroll 1
@@ -458,6 +487,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    // this warp's tcgen05.ld of the accumulator are complete: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+    }  // tile loop
   }
   tc_fence_before();
   __syncthreads();
@@ -465,6 +499,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
 }
 
 template <int MODE, int BN, int MSUB, typename TOp>
@@ -479,8 +523,10 @@ static int launch_tc(const void* A, const void* Bw, int M, int N, int K, const E
                                        Cfg::kSmem));
     attr_done = true;
   }
-  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM * MSUB));
-  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, ep);
+  const int tiles_m = cdiv(M, TC_BM * MSUB), tiles_n = cdiv(N, BN);
+  const int total = tiles_m * tiles_n;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, tiles_m, tiles_n, ep);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
@@ -501,12 +547,13 @@ static TileChoice choose_tile(int mode, int M, int N, int K, int esz, bool opera
     if (t.bn == 64 && esz == 2 && (mode != EPI_LINEAR || operand_dest)) continue;   // needs 64-column row segments
     if (t.bn > 64 && N <= t.bn / 2) continue;                // mostly empty tile
     const long tiles = (long)cdiv(M, 128 * t.msub) * cdiv(N, t.bn);
-    const long per_sm = (tiles + 147) / 148;
+    const long per_sm = (tiles + 147) / 148;                 // tiles of the busiest persistent CTA
     const double cta_macs = (double)t.msub * 128.0 * t.bn * K;
     const double t_mma = per_sm * cta_macs / mac_per_cycle;
     const double bytes = (double)tiles * ((double)t.msub * 128 + t.bn) * K * esz;
     const double t_l2 = bytes / l2_bytes_per_cycle;
-    const double t_epi = per_sm * (double)t.msub * t.bn * 6.0 + 2500.0;   // drain + launch/prologue latency
+    const double acc2 = (2 * t.msub * t.bn <= 512) ? 0.15 : 1.0;         // double-buffered accumulators hide the drain
+    const double t_epi = (acc2 * per_sm + (1.0 - acc2)) * (double)t.msub * t.bn * 4.0 + 3000.0;
     const double est = (t_mma > t_l2 ? t_mma : t_l2) + t_epi;
     if (est < best) { best = est; pick = t; }
   }
