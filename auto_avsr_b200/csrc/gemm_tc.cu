@@ -220,7 +220,7 @@ template <> struct OpTraits<__half> {
 template <int MODE, int BN, int MSUB, typename TOp>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_m,
-               int tiles_n, EpiParams ep) {
+               int tiles_n, int splits, EpiParams ep) {
   // PERSISTENT: CTA c processes tiles c, c + gridDim.x, ... (n fastest, so concurrently running CTAs share A rows in
   // L2).  The TMA ring never drains between tiles and the accumulator is double-buffered in TMEM, so the epilogue of
   // tile i overlaps the main loop of tile i+1 (at K = 768 a tile is only 12 k-blocks: per-tile prologue / pipeline
@@ -246,6 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / KE;
   const int total_tiles = tiles_m * tiles_n;
+  // split-K (LINEAR into the residual stream only): work item = (tile, K-slice); slice-major order so that CTAs
+  // running at the same time reduce into different tiles.  Partial sums are added with red.global.add.v4.f32.
+  const int total_items = total_tiles * splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -263,9 +266,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;                                       // running k-block counter across tiles
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tile = item % total_tiles, split = item / total_tiles;
         const int m0 = (tile / tiles_n) * (TC_BM * MSUB), n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int kb0 = split * nkb / splits, kb1 = (split + 1) * nkb / splits;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
@@ -282,13 +287,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = Op::idesc(TC_BM, BN);
       int it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++t) {
+        const int split = item / total_tiles;
+        const int kb0 = split * nkb / splits, kb1 = (split + 1) * nkb / splits;
         const int acc = (ACC == 2) ? (t & 1) : 0;
         const uint32_t acc_ph = ((ACC == 2) ? (t >> 1) : t) & 1;
         mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);     // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * (MSUB * BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(full_bar(s), ph);
@@ -300,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
-              Op::mma(tacc + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              Op::mma(tacc + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0) || (k != 0));
           }
           tc_commit(empty_bar(s));
         }
@@ -318,7 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int ONE = 16 / (int)sizeof(TOp);               // operand elements per 16-byte piece
     int t = 0;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++t) {
+    const int tile = item % total_tiles, split = item / total_tiles;
     const int m0 = (tile / tiles_n) * (TC_BM * MSUB), n0 = (tile % tiles_n) * BN;
     const int acc = (ACC == 2) ? (t & 1) : 0;
     const uint32_t acc_ph = ((ACC == 2) ? (t >> 1) : t) & 1;
@@ -333,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n = n0 + c;
         float bv = 0.f, uv = 0.f, vv = 0.f;
         if constexpr (MODE != EPI_VT && MODE != EPI_POS) {
-          if (ep.bias && n < ep.N) bv = ep.bias[n];
+          if (ep.bias && n < ep.N && split == 0) bv = ep.bias[n];   // split-K: the bias is added by slice 0 only
         }
         if constexpr (MODE == EPI_QK) {
           if (n < D) { uv = ep.pos_u[n]; vv = ep.pos_v[n]; }
@@ -379,9 +387,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
             stage_write_f32(stg, lane, v, false);
             __syncwarp();
+            const int n = n0 + c + pc * 4;
+            if (splits > 1) {
+              // split-K: out (== the residual stream) += alpha * partial, one 16-byte vector reduction per lane
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int m = mw + it * 4 + pr;
+                const uint4 pay = stage_read(stg, it, lane);
+                const float4 o = *reinterpret_cast<const float4*>(&pay);
+                if (m < ep.M && n < ep.N) {
+                  float* dst = reinterpret_cast<float*>(ep.out) + (long)m * ep.ldo + n;
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(ep.alpha * o.x),
+                               "f"(ep.alpha * o.y), "f"(ep.alpha * o.z), "f"(ep.alpha * o.w)
+                               : "memory");
+                }
+              }
+            } else {
             // residual pieces first (8 independent coalesced loads in flight), then combine + store: a load may not
             // be hoisted above a store by the compiler (possible aliasing), so the order is made explicit here
-            const int n = n0 + c + pc * 4;
             float4 r[8];
             if (ep.resid) {
 #pragma unroll
@@ -402,6 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               if (m < ep.M && n < ep.N)
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long)m * ep.ldo + n) = o;
+            }
             }
             __syncwarp();
           }
@@ -512,7 +536,8 @@ static int num_sms() {
 }
 
 template <int MODE, int BN, int MSUB, typename TOp>
-static int launch_tc(const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+static int launch_tc(const void* A, const void* Bw, int M, int N, int K, int splits, const EpiParams& ep,
+                     cudaStream_t st) {
   using Cfg = TcCfg<BN, MSUB>;
   CUtensorMap tmA, tmB;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, TC_BM, (int)sizeof(TOp)));
@@ -524,38 +549,49 @@ static int launch_tc(const void* A, const void* Bw, int M, int N, int K, const E
     attr_done = true;
   }
   const int tiles_m = cdiv(M, TC_BM * MSUB), tiles_n = cdiv(N, BN);
-  const int total = tiles_m * tiles_n;
+  const int total = tiles_m * tiles_n * splits;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, tiles_m, tiles_n, ep);
+  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, tiles_m, tiles_n, splits, ep);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
 
-// ---------------------------------------------------------------- tile selection
-// Estimated time of one GEMM for tile (MSUB*128) x BN on 148 SMs: the busiest SM's tensor-pipe time vs the bytes
-// every CTA pulls through L2 (operands are re-read once per tile row/column), plus a per-tile epilogue term.
-struct TileChoice { int bn, msub; };
-static const TileChoice kTiles[] = {{64, 1}, {128, 1}, {128, 2}, {256, 1}, {256, 2}};
+// ---------------------------------------------------------------- tile / split selection
+// Cost model (SM cycles) of one GEMM on 148 persistent CTAs.  What the r01 profiles showed: an SM ingests only
+// ~46 B/cycle through TMA (B300_MICROARCH "TMA service/SM"; measured 32 KB per ~690 cycles), well below what the
+// tensor pipe consumes, so time ~ (bytes pulled by the busiest SM) / 46 unless the tensor pipe is slower; the
+// epilogue hides behind the next item when the accumulator is double-buffered.  Split-K (only for GEMMs that
+// accumulate into the fp32 residual stream) spreads a long K over more SMs.
+struct TileChoice { int bn, msub, splits; };
+static const int kTileShapes[][2] = {{64, 1}, {128, 1}, {128, 2}, {256, 1}, {256, 2}};
 
-static TileChoice choose_tile(int mode, int M, int N, int K, int esz, bool operand_dest) {
+static TileChoice choose_tile(int mode, int M, int N, int K, int esz, bool operand_dest, bool can_split) {
   const double mac_per_cycle = esz == 2 ? 4096.0 : 2048.0;   // per SM, dense f16 / tf32
-  const double l2_bytes_per_cycle = 6000.0;                  // chip-wide L2->SM bytes per SM-clock (>= 11 TB/s observed)
+  const double ingest = 46.0;                                // TMA bytes per cycle per SM
+  const int nkb = K / (128 / esz);
+  const int sms = 148;
   double best = 1e30;
-  TileChoice pick = kTiles[0];
-  for (const TileChoice& t : kTiles) {
-    if (mode == EPI_GLU && t.bn % 128 != 0) continue;
-    if (t.bn == 64 && esz == 2 && (mode != EPI_LINEAR || operand_dest)) continue;   // needs 64-column row segments
-    if (t.bn > 64 && N <= t.bn / 2) continue;                // mostly empty tile
-    const long tiles = (long)cdiv(M, 128 * t.msub) * cdiv(N, t.bn);
-    const long per_sm = (tiles + 147) / 148;                 // tiles of the busiest persistent CTA
-    const double cta_macs = (double)t.msub * 128.0 * t.bn * K;
-    const double t_mma = per_sm * cta_macs / mac_per_cycle;
-    const double bytes = (double)tiles * ((double)t.msub * 128 + t.bn) * K * esz;
-    const double t_l2 = bytes / l2_bytes_per_cycle;
-    const double acc2 = (2 * t.msub * t.bn <= 512) ? 0.15 : 1.0;         // double-buffered accumulators hide the drain
-    const double t_epi = (acc2 * per_sm + (1.0 - acc2)) * (double)t.msub * t.bn * 4.0 + 3000.0;
-    const double est = (t_mma > t_l2 ? t_mma : t_l2) + t_epi;
-    if (est < best) { best = est; pick = t; }
+  TileChoice pick{128, 1, 1};
+  for (const auto& sh : kTileShapes) {
+    const int bn = sh[0], msub = sh[1];
+    if (mode == EPI_GLU && bn % 128 != 0) continue;
+    if (bn == 64 && esz == 2 && (mode != EPI_LINEAR || operand_dest)) continue;   // needs 64-column row segments
+    if (bn > 64 && N <= bn / 2) continue;                                          // mostly empty tile
+    const long tiles = (long)cdiv(M, 128 * msub) * cdiv(N, bn);
+    for (int splits = 1; splits <= (can_split ? 8 : 1); ++splits) {
+      if (splits > nkb) break;
+      const long items = tiles * splits;
+      const long per_sm = (items + sms - 1) / sms;
+      const double kfrac = (double)((nkb + splits - 1) / splits) * (128 / esz);    // K elements of the longest slice
+      const double t_mma = per_sm * (double)msub * 128.0 * bn * kfrac / mac_per_cycle;
+      const double t_in = per_sm * ((double)msub * 128 + bn) * kfrac * esz / ingest;
+      const bool acc2 = 2 * msub * bn <= 512;
+      const double drain = (double)msub * bn * 10.0;                               // one item's epilogue
+      const double t_epi = acc2 ? drain : per_sm * drain;
+      const double t_red = splits > 1 ? per_sm * (double)msub * bn * 4.0 : 0.0;    // reductions instead of stores
+      const double est = (t_mma > t_in ? t_mma : t_in) + t_epi + t_red + 4000.0;
+      if (est < best) { best = est; pick = TileChoice{bn, msub, splits}; }
+    }
   }
   return pick;
 }
@@ -564,12 +600,12 @@ template <int MODE, typename TOp>
 static int dispatch_tile(TileChoice t, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
                          cudaStream_t st) {
   if (t.bn == 64) {
-    if constexpr (MODE != EPI_GLU) return launch_tc<MODE, 64, 1, TOp>(A, Bw, M, N, K, ep, st);
+    if constexpr (MODE != EPI_GLU) return launch_tc<MODE, 64, 1, TOp>(A, Bw, M, N, K, t.splits, ep, st);
   }
-  if (t.bn == 128 && t.msub == 1) return launch_tc<MODE, 128, 1, TOp>(A, Bw, M, N, K, ep, st);
-  if (t.bn == 128 && t.msub == 2) return launch_tc<MODE, 128, 2, TOp>(A, Bw, M, N, K, ep, st);
-  if (t.bn == 256 && t.msub == 1) return launch_tc<MODE, 256, 1, TOp>(A, Bw, M, N, K, ep, st);
-  if (t.bn == 256 && t.msub == 2) return launch_tc<MODE, 256, 2, TOp>(A, Bw, M, N, K, ep, st);
+  if (t.bn == 128 && t.msub == 1) return launch_tc<MODE, 128, 1, TOp>(A, Bw, M, N, K, t.splits, ep, st);
+  if (t.bn == 128 && t.msub == 2) return launch_tc<MODE, 128, 2, TOp>(A, Bw, M, N, K, t.splits, ep, st);
+  if (t.bn == 256 && t.msub == 1) return launch_tc<MODE, 256, 1, TOp>(A, Bw, M, N, K, t.splits, ep, st);
+  if (t.bn == 256 && t.msub == 2) return launch_tc<MODE, 256, 2, TOp>(A, Bw, M, N, K, t.splits, ep, st);
   set_error("gemm_tc: no kernel for tile %dx%d", t.msub * 128, t.bn);
   return AVSR_E_INVALID;
 }
@@ -578,12 +614,21 @@ template <typename TOp>
 static int dispatch_mode(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep,
                          cudaStream_t st) {
   const bool operand_dest = mode != EPI_GLU && (mode != EPI_LINEAR || ep.round_out != 0);
-  TileChoice t = choose_tile(mode, M, N, K, (int)sizeof(TOp), operand_dest);
-  if (const char* force = getenv("AVSR_B200_TILE")) {        // "BN,MSUB" -- tuning / profiling aid
-    int bn = 0, ms = 0;
-    if (sscanf(force, "%d,%d", &bn, &ms) == 2 && (mode != EPI_GLU || bn % 128 == 0) &&
-        !(bn == 64 && sizeof(TOp) == 2 && operand_dest))
-      t = TileChoice{bn, ms};
+  // split-K adds partial sums into the destination: only when the destination IS the residual it accumulates into
+  // Opt-in (AVSR_B200_SPLITK=1): fp32 atomics make the summation order -- hence the last bits of x, and after 12
+  // layers of 11-bit operand rounding ~2e-3 of the output -- vary from run to run; measured gain at S2 is 2.4 %.
+  static const bool allow_split = [] { const char* e = getenv("AVSR_B200_SPLITK"); return e && e[0] == '1'; }();
+  const bool can_split = allow_split && mode == EPI_LINEAR && !ep.round_out && !ep.relu && ep.resid != nullptr &&
+                         ep.resid == reinterpret_cast<const float*>(ep.out);
+  TileChoice t = choose_tile(mode, M, N, K, (int)sizeof(TOp), operand_dest, can_split);
+  if (const char* force = getenv("AVSR_B200_TILE")) {        // "BN,MSUB[,SPLITS]" -- tuning / profiling aid
+    int bn = 0, ms = 0, sp = 1;
+    const int got = sscanf(force, "%d,%d,%d", &bn, &ms, &sp);
+    if (got >= 2 && (mode != EPI_GLU || bn % 128 == 0) && !(bn == 64 && sizeof(TOp) == 2 && operand_dest)) {
+      if (got < 3 || !can_split || sp < 1) sp = 1;
+      const int nkb = K / (128 / (int)sizeof(TOp));
+      t = TileChoice{bn, ms, sp > nkb ? nkb : sp};
+    }
   }
   AVSR_REQUIRE(mode == EPI_VT || N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", N);
   if (mode == EPI_LINEAR) {

@@ -280,3 +280,25 @@ def test_launch_counter_counts_kernels(dev):
     before = _cabi.launch_count()
     ops.layernorm(torch.randn(4, 768, device=dev), torch.ones(768, device=dev), torch.zeros(768, device=dev))
     assert _cabi.launch_count() == before + 1
+
+
+def test_split_k_opt_in_is_within_tolerance(dev):
+    """AVSR_B200_SPLITK=1 (fp32-atomic split-K of the K=3072 GEMMs) is read once per process: run it in a child."""
+    import subprocess, sys, os
+    code = """
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from helpers import load_case, err_stats
+from auto_avsr_b200 import ConformerEncoder
+from oracle import conformer_oracle as O
+c = load_case("full12_ragged")
+enc = ConformerEncoder(); enc.load_state_dict(c["sd"]); enc = enc.cuda().eval(); enc.precision = "f16"
+mask = O.non_pad_mask(c["lengths"]).unsqueeze(1).cuda()
+out = enc(c["xs"].cuda(), mask)[0].cpu()
+mx, rms = err_stats(out, torch.from_numpy(c["z"]["out_f64"]))
+print("SPLITK", mx, rms)
+assert mx < 2e-2 and rms < 3e-3
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, AVSR_B200_SPLITK="1"), timeout=300)
+    assert r.returncode == 0 and "SPLITK" in r.stdout, r.stdout + r.stderr[-1500:]
