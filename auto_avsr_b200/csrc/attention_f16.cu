@@ -64,8 +64,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * AH_BQ, h = blockIdx.y, b = blockIdx.z;
   const int bh = b * H + h;
+  pdl_launch_dependents();
   int L = T;
-  if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }
+  if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }   // lengths: written before the graph, not by the predecessor
   const int nkt = (L + AH_BKV - 1) / AH_BKV;
 
   if (threadIdx.x == 0) {
@@ -80,6 +81,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -267,8 +269,7 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
     attr_done = true;
   }
   dim3 grid(cdiv(T, AH_BQ), H, B);
-  attention_f16_kernel<<<grid, AH_THREADS, AH_SMEM, st>>>(tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
   return AVSR_OK;
 }
 

@@ -63,8 +63,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
   const int bh = b * H + h;
+  pdl_launch_dependents();
   int L = T;
-  if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }
+  if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }   // lengths: written before the graph, not by the predecessor
   const int nkt = (L + AT_BKV - 1) / AT_BKV;
 
   if (threadIdx.x == 0) {
@@ -79,6 +80,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -262,8 +264,7 @@ int attention_tc(const float* qu, const float* qv, const float* kk, const float*
     attr_done = true;
   }
   dim3 grid(cdiv(T, AT_BQ), H, B);
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H, round_out);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(attention_tc_kernel, grid, AT_THREADS, AT_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H, round_out);
   return AVSR_OK;
 }
 

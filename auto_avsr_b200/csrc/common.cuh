@@ -6,7 +6,10 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <string>
+#include <tuple>
+#include <utility>
 
 #include "../../include/avsr_b200.h"
 
@@ -49,6 +52,48 @@ constexpr int kHeadDim = 64;  // d_k of the reference encoder (768 / 12); the at
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start (block
+// scheduling, barrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the stream / graph is
+// still draining, and blocks in pdl_wait() until the predecessor has completed and flushed before it touches any
+// global memory.  pdl_launch_dependents() at the top lets the successor do the same.  Without the attribute both
+// are no-ops, so the same kernels work under plain launches (AVSR_B200_PDL=0).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("AVSR_B200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args, size_t... I>
+inline cudaError_t launch_kernel_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      std::index_sequence<I...>, Args&&... args) {
+  std::tuple<KArgs...> params(static_cast<KArgs>(args)...);
+  void* ptrs[] = {const_cast<void*>(static_cast<const void*>(&std::get<I>(params)))...};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), ptrs);
+}
+// launch `kernel<<<grid, block, smem, st>>>(args...)` with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "kernel argument count mismatch");
+  return launch_kernel_impl(kernel, grid, block, smem, st, std::index_sequence_for<KArgs...>{}, std::forward<Args>(args)...);
+}
+
+#define AVSR_LAUNCH(kernel, grid, block, smem, st, ...)                                                \
+  do {                                                                                                 \
+    ::avsr::g_launches.fetch_add(1);                                                                   \
+    AVSR_CUDA_TRY(::avsr::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)); \
+  } while (0)
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float round_tf32(float x) {

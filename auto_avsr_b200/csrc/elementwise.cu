@@ -9,6 +9,8 @@ namespace avsr {
 
 // ------------------------------------------------------------------ embed: x = xs * sqrt(d)   (embedding.py:178)
 __global__ void embed_scale_kernel(const float4* __restrict__ xs, float4* __restrict__ x, long n4, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 v = xs[i];
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
@@ -22,8 +24,7 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  embed_scale_kernel<<<blocks, 256, 0, st>>>((const float4*)xs, (float4*)x, n4, scale);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(embed_scale_kernel, blocks, 256, 0, st, (const float4*)xs, (float4*)x, n4, scale);
   return AVSR_OK;
 }
 
@@ -35,11 +36,22 @@ constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         int rows, int d, int out_kind) {
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
   const int nvec = d >> 2;
+  // gamma / beta are parameters (not produced by the previous kernel): fetch them before waiting on it
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 gg[kLnMaxVec], bb[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) { gg[i] = g4[c]; bb[i] = b4[c]; }
+  }
+  pdl_wait();
   float4 v[kLnMaxVec];
   float s = 0.f;
 #pragma unroll
@@ -61,13 +73,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int c = i * 32 + lane;
     if (c < nvec) {
-      const float4 g = g4[c], b = b4[c];
+      const float4 g = gg[i], b = bb[i];
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x;
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -84,8 +94,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* y, in
                kLnMaxVec * 128);
   if (rows <= 0) return AVSR_OK;
   const int warps_per_block = 8;
-  layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, st>>>(x, g, b, y, rows, d, out_kind);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(layernorm_kernel, cdiv(rows, warps_per_block), warps_per_block * 32, 0, st, x, g, b, y, rows, d, out_kind);
   return AVSR_OK;
 }
 
@@ -94,6 +103,8 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* y, in
 // The reference evaluates everything in fp32: the frequency is a correctly rounded fp32 exp, the
 // argument an fp32 product; sinf/cosf here take the full-range (non fast-math) path.
 __global__ void sinusoid_kernel(void* __restrict__ pe, int T, int d, int out_kind) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = d >> 1;
   const long total = (long)(2 * T - 1) * half;
   const float step = (float)(-(log(10000.0) / (double)d));
@@ -121,8 +132,7 @@ int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st) {
   const long total = (long)(2 * T - 1) * (d / 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sinusoid_kernel<<<blocks, 256, 0, st>>>(pe, T, d, out_kind);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(sinusoid_kernel, blocks, 256, 0, st, pe, T, d, out_kind);
   return AVSR_OK;
 }
 
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __rest
                                                              const float* __restrict__ shift, void* __restrict__ y,
                                                              int T, int C, int K, int out_kind) {
   extern __shared__ float4 dw_smem[];
+  pdl_launch_dependents();
   const int rows_in = kDwTT + K - 1;
   float4* in_s = dw_smem;                          // [rows_in][16]
   float4* w_s = dw_smem + rows_in * (kDwCh / 4);   // [K][16]
@@ -150,19 +161,21 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __rest
   const int tid = threadIdx.x;
   const float* xb = x + (long)b * T * C;
 
-  for (int i = tid; i < rows_in * (kDwCh / 4); i += 256) {
-    const int r = i >> 4, q = i & 15;
-    const int t = t0 - half + r, c = c0 + q * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T && c < C) v = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
-    in_s[i] = v;
-  }
+  // the taps are parameters: stage them before waiting on the producer of x
   for (int i = tid; i < K * (kDwCh / 4); i += 256) {
     const int k = i >> 4, q = i & 15;
     const int c = c0 + q * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) v = *reinterpret_cast<const float4*>(wt + (long)k * C + c);
     w_s[i] = v;
+  }
+  pdl_wait();
+  for (int i = tid; i < rows_in * (kDwCh / 4); i += 256) {
+    const int r = i >> 4, q = i & 15;
+    const int t = t0 - half + r, c = c0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T && c < C) v = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
+    in_s[i] = v;
   }
   __syncthreads();
 
@@ -198,8 +211,7 @@ int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, c
   if (smem > 48 * 1024)
     AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(C, kDwCh), cdiv(T, kDwTT), B);
-  dwconv_bn_silu_kernel<<<grid, 256, smem, st>>>(x, wt, scale, shift, y, T, C, K, out_kind);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH(dwconv_bn_silu_kernel, grid, 256, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
   return AVSR_OK;
 }
 

@@ -250,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // running at the same time reduce into different tiles.  Partial sums are added with red.global.add.v4.f32.
   const int total_items = total_tiles * splits;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -262,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   if (warp == 0) {
     if (lane == 0) {
@@ -551,8 +553,7 @@ static int launch_tc(const void* A, const void* Bw, int M, int N, int K, int spl
   const int tiles_m = cdiv(M, TC_BM * MSUB), tiles_n = cdiv(N, BN);
   const int total = tiles_m * tiles_n * splits;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<MODE, BN, MSUB, TOp><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmB, K, tiles_m, tiles_n, splits, ep);
-  AVSR_CHECK_LAUNCH();
+  AVSR_LAUNCH((gemm_tc_kernel<MODE, BN, MSUB, TOp>), grid, TC_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_m, tiles_n, splits, ep);
   return AVSR_OK;
 }
 
