@@ -248,6 +248,8 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 // `out_kind` is an OperandKind: how y / pe is stored
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st);
+int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
+                      void* y2, int rows, int d, int out_kind, cudaStream_t st);
 int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st);
 int launch_dwconv_bn_silu(const float* x, const float* wt /*(K,C)*/, const float* scale, const float* shift, void* y,
                           int B, int T, int C, int K, int out_kind, cudaStream_t st);

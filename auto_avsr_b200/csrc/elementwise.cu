@@ -33,8 +33,8 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 // Two-pass mean / centred variance, warp-shuffle reductions.
 constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, void* __restrict__ y,
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may alias y */, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, void* y,
                                                         int rows, int d, int out_kind) {
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -86,6 +86,95 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       store_kind4(y, (long)warp * d + 4 * c, out_kind, o.x, o.y, o.z, o.w);
     }
   }
+}
+
+// Two chained LayerNorms in one pass over the row: y1 = LN(x; g1, b1) (fp32, may alias x) and
+// y2 = LN(y1; g2, b2) in operand storage -- layer l's norm_final followed by layer l+1's norm_ff_macaron
+// (conformer_encoder.py:161-162 then :113): one read of x instead of two, one launch instead of two.
+__global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may alias y1 */, const float* __restrict__ g1,
+                                                         const float* __restrict__ b1, const float* __restrict__ g2,
+                                                         const float* __restrict__ b2, float* y1,
+                                                         void* __restrict__ y2, int rows, int d, int out_kind) {
+  pdl_launch_dependents();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = d >> 2;
+  const float4* g14 = reinterpret_cast<const float4*>(g1);
+  const float4* b14 = reinterpret_cast<const float4*>(b1);
+  float4 gg[kLnMaxVec], bb[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) { gg[i] = g14[c]; bb[i] = b14[c]; }
+  }
+  pdl_wait();
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  }
+  float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
+  float4* y1r = reinterpret_cast<float4*>(y1 + (long)warp * d);
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      v[i].x = (v[i].x - mean) * rstd * gg[i].x + bb[i].x;
+      v[i].y = (v[i].y - mean) * rstd * gg[i].y + bb[i].y;
+      v[i].z = (v[i].z - mean) * rstd * gg[i].z + bb[i].z;
+      v[i].w = (v[i].w - mean) * rstd * gg[i].w + bb[i].w;
+      y1r[c] = v[i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float4* g24 = reinterpret_cast<const float4*>(g2);
+  const float4* b24 = reinterpret_cast<const float4*>(b2);
+  mean = warp_sum(s) / (float)d;
+  q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      gg[i] = g24[c]; bb[i] = b24[c];
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec)
+      store_kind4(y2, (long)warp * d + 4 * c, out_kind, (v[i].x - mean) * rstd * gg[i].x + bb[i].x,
+                  (v[i].y - mean) * rstd * gg[i].y + bb[i].y, (v[i].z - mean) * rstd * gg[i].z + bb[i].z,
+                  (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
+  }
+}
+
+int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
+                      void* y2, int rows, int d, int out_kind, cudaStream_t st) {
+  AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm2: d=%d must be a multiple of 4 and <= %d", d,
+               kLnMaxVec * 128);
+  if (rows <= 0) return AVSR_OK;
+  const int warps_per_block = 8;
+  AVSR_LAUNCH(layernorm2_kernel, cdiv(rows, warps_per_block), warps_per_block * 32, 0, st, x, g1, b1, g2, b2, y1, y2,
+              rows, d, out_kind);
+  return AVSR_OK;
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,

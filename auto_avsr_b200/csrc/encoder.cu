@@ -214,7 +214,8 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       return AVSR_OK;
     };
     // (1) macaron FFN: x += 0.5 * w2(relu(w1 LN(x)))                         conformer_encoder.py:110-116
-    AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
+    // (for l > 0 the norm_ff_macaron output was produced together with the previous layer's norm_final)
+    if (l == 0) AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, opr), st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_linear(N, D, w.ffm_b2, W.x, W.x, 0.5f, 0, 0), st));
     AVSR_TRY(tap(0));
@@ -257,7 +258,13 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_linear(N, D, w.ff_b2, W.x, W.x, 0.5f, 0, 0), st));
     AVSR_TRY(tap(3));
     // (5) x = LN_final(x)                                                     conformer_encoder.py:161-162
-    AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st));
+    //     fused with the next layer's norm_ff_macaron: one pass writes x (fp32) and xn (operand)
+    if (l + 1 < L) {
+      const LayerPrep& nx = P.layers[l + 1];
+      AVSR_TRY(launch_layernorm2(W.x, w.ln_fin_w, w.ln_fin_b, nx.ln_ffm_w, nx.ln_ffm_b, W.x, W.xn, N, D, opk, st));
+    } else {
+      AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st));
+    }
     AVSR_TRY(tap(4));
   }
   return AVSR_OK;
