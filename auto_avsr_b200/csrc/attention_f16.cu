@@ -159,9 +159,15 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       const int j0 = it * AH_BKV + hf * 64;       // first key this thread scores
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      float s[64];
+      float s[64];   // raw (unscaled) scores of this thread's 64 keys
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
+        const int jc = j0 + c0;                   // first key of this 32-key chunk (warp-uniform)
+        if (jc >= L) {                            // chunk entirely beyond the utterance: no loads, no skew, no exp
+#pragma unroll
+          for (int c = 0; c < 32; ++c) s[c0 + c] = -INFINITY;
+          continue;
+        }
         float x[64];
         tmem_ld32(trow + TH_G + gbase + hf * 64 + c0, x);
         tmem_ld32(trow + TH_G + gbase + hf * 64 + c0 + 32, x + 32);
@@ -188,10 +194,12 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 32; ++c) x[c] = x[c + 1];
         }
+        if (jc + 32 <= L) {                       // fully valid chunk: no per-key mask
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float v = (s[c0 + c] + x[c]) * kScale;
-          s[c0 + c] = (j0 + c0 + c < L) ? v : -INFINITY;
+          for (int c = 0; c < 32; ++c) s[c0 + c] += x[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) s[c0 + c] = (jc + c < L) ? s[c0 + c] + x[c] : -INFINITY;
         }
       }
       float mloc = -INFINITY;
@@ -201,17 +209,20 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       float* slot = xch + (it & 1) * 256;
       slot[hf * 128 + r] = mloc;
       named_bar_sync(1 + q, 64);
-      const float mx = fmaxf(m_run, fmaxf(mloc, slot[(hf ^ 1) * 128 + r]));   // finite: key j0_tile+0 < L is valid
-      const float alpha = exp2f(m_run - mx);      // first tile: exp2(-inf) = 0
+      const float mx = fmaxf(m_run, fmaxf(mloc, slot[(hf ^ 1) * 128 + r]));   // finite: key (tile start) < L is valid
+      const float alpha = exp2f((m_run - mx) * kScale);   // first tile: exp2(-inf) = 0
       m_run = mx;
+      const float mxs = mx * kScale;
       float sum = 0.f;
       // P row (64 halves = 128 B = one atom row) -> shared as fp16, 16-byte chunk index XOR (r & 7)
+      // p = exp2(s * kScale - mx * kScale): scale folded into one FFMA per element
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(s[8 * ch + 2 * e] - mx), p1 = exp2f(s[8 * ch + 2 * e + 1] - mx);
+          const float p0 = exp2f(fmaf(s[8 * ch + 2 * e], kScale, -mxs));
+          const float p1 = exp2f(fmaf(s[8 * ch + 2 * e + 1], kScale, -mxs));
           sum += p0 + p1;
           const __half2 hp = __floats2half2_rn(p0, p1);
           pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
