@@ -14,6 +14,8 @@
 //        part) + 5-stage barrel shifter (per-lane part), scale, key mask, online max (halves exchanged through
 //        shared memory + a 64-thread named barrier), exp2, P -> shared memory as fp16 in UMMA SWIZZLE_128B layout
 //   MMA  O'[128 x 64] = P . V_tile            8 x tcgen05.mma M128 N64 K16       TMEM cols 384..447
+//        V stays in its natural (B,H,T,64) layout: the V tile [128 keys][64 d] is the B operand in MN-major form
+//        (N = d contiguous), so the QKV projection is ONE GEMM and no transpose of V is ever materialised
 //        rescale-accumulated into registers (each thread owns 32 of the 64 output channels of its row)
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 softmax/epilogue.
 // Padded QUERY rows are computed like any other row (the reference masks keys only).
@@ -33,8 +35,8 @@ constexpr int AH_THREADS = 320;
 constexpr int AH_QU = 0;                          // [128][128B]
 constexpr int AH_QV = AH_QU + AH_BQ * 128;        // 16384
 constexpr int AH_K = AH_QV + AH_BQ * 128;         // 32768   [128 keys][128B]
-constexpr int AH_V = AH_K + AH_BKV * 128;         // 49152   2 atoms x [64 d][128B = 64 keys]
-constexpr int AH_PB = AH_V + 2 * 64 * 128;        // 65536   [256][128B]
+constexpr int AH_V = AH_K + AH_BKV * 128;         // 49152   [128 keys][128B = 64 d]  (MN-major B operand)
+constexpr int AH_PB = AH_V + AH_BKV * 128;        // 65536   [256][128B]
 constexpr int AH_P = AH_PB + AH_BAND * 128;       // 98304   2 atoms x [128 rows][128B = 64 keys]
 constexpr int AH_XCH = AH_P + 2 * AH_BQ * 128;    // 131072  float [2 slots][2 halves][128 rows]
 constexpr int AH_BARS = AH_XCH + 2 * 2 * 128 * 4; // 133120
@@ -97,9 +99,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         const int m_lo = j0 - i0 - (AH_BQ - 1) + T - 1;       // first table row of the band (may be < 0: zero fill)
         tma_load_3d(base + AH_PB, &tmP, 0, m_lo, h, kp_full);
         if (it > 0) mbar_wait(o_full, (it - 1) & 1);          // P.V of the previous tile retired: V free
-        mbar_expect_tx(v_full, 2 * 64 * 128);
-        tma_load_2d(base + AH_V, &tmV, j0, bh * 64, v_full);
-        tma_load_2d(base + AH_V + 64 * 128, &tmV, j0 + 64, bh * 64, v_full);
+        mbar_expect_tx(v_full, AH_BKV * 128);
+        tma_load_2d(base + AH_V, &tmV, 0, bh * T + j0, v_full);
       }
     }
   } else if (warp == 1) {
@@ -107,7 +108,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
     if (lane == 0 && nkt > 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AH_BQ, AH_BKV);
       constexpr uint32_t idesc_g = umma_idesc_f16(AH_BQ, AH_BAND);
-      constexpr uint32_t idesc_o = umma_idesc_f16(AH_BQ, 64);
+      constexpr uint32_t idesc_o = umma_idesc_f16_bmn(AH_BQ, 64);
       auto issue_scores = [&]() {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)   // d_k = 64 halves = 4 MMA-K steps of 32 bytes inside one atom
@@ -128,9 +129,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         mbar_wait(v_full, it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)   // 128 keys = 2 atoms x 4 steps
+        for (int ks = 0; ks < 8; ++ks)   // A = P: 2 K-major atoms x 4 steps; B = V: 16 key rows (2 KB) per step
           mma_f16(tmem + TH_O, umma_desc_sw128(base + AH_P + (ks >> 2) * (AH_BQ * 128) + (ks & 3) * 32),
-                  umma_desc_sw128(base + AH_V + (ks >> 2) * (64 * 128) + (ks & 3) * 32), idesc_o, ks != 0);
+                  umma_desc_sw128(base + AH_V + ks * (16 * 128)), idesc_o, ks != 0);
         tc_commit(o_full);
         if (it + 1 < nkt) {
           mbar_wait(kp_full, (it + 1) & 1);
@@ -263,16 +264,16 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   }
 }
 
-int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vt, const __half* pos,
-                  const int32_t* lengths, __half* ctx, int B, int T, int H, int Tp, int Rp, cudaStream_t st) {
-  AVSR_REQUIRE(Tp % 8 == 0 && Tp >= T && Rp >= 2 * T - 1, "attention_f16: bad Tp=%d Rp=%d for T=%d", Tp, Rp, T);
+int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vv, const __half* pos,
+                  const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st) {
+  AVSR_REQUIRE(Rp >= 2 * T - 1, "attention_f16: bad Rp=%d for T=%d", Rp, T);
   if (B <= 0 || T <= 0) return AVSR_OK;
   CUtensorMap tmQu, tmQv, tmK, tmV, tmP;
   const uint64_t rows = (uint64_t)B * H * T;
   AVSR_TRY(make_tmap_2d(&tmQu, qu, rows, 64, 64, AH_BQ, 2));
   AVSR_TRY(make_tmap_2d(&tmQv, qv, rows, 64, 64, AH_BQ, 2));
   AVSR_TRY(make_tmap_2d(&tmK, kk, rows, 64, 64, AH_BKV, 2));
-  AVSR_TRY(make_tmap_2d(&tmV, vt, (uint64_t)B * H * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 2));
+  AVSR_TRY(make_tmap_2d(&tmV, vv, rows, 64, 64, AH_BKV, 2));
   AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AH_BAND, 2));
   static bool attr_done = false;
   if (!attr_done) {

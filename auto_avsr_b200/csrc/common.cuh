@@ -161,7 +161,8 @@ __device__ __forceinline__ void store_kind4(void* base, long idx, int kind, floa
 // Every GEMM computes acc[m][n] = sum_k A[m][k] * Bw[n][k]  (both operands K-major, i.e. torch Linear).
 enum EpiMode : int {
   EPI_LINEAR = 0,  // y = [resid + alpha *] act(acc + bias[n])                      -> out (M, ldo)
-  EPI_QK = 1,      // n <  D: q -> qu = q+bias+pos_u, qv = q+bias+pos_v ; n >= D: k   -> (B,H,T,64) each
+  EPI_QK = 1,      // n <  D: q -> qu = q+bias+pos_u, qv = q+bias+pos_v ; D <= n < 2D: k ; 2D <= n < 3D (when
+                   // N == 3D): v into `vt` with the SAME head-major layout   -> (B,H,T,64) each
   EPI_VT = 2,      // A = W_v (m = feature), B = frames (n): v^T                     -> (B,H,64,Tp)
   EPI_GLU = 3,     // interleaved pointwise_cov1: value cols [g*128, +64), gate cols +64 -> out (M, N/2)
   EPI_POS = 4      // linear_pos of all layers: n = l*D + h*64 + d, m = table row      -> (L,H,Rp,64)
@@ -205,15 +206,15 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, int m, int n, floa
   } else if constexpr (MODE == EPI_QK) {
     const int D = p.H * kHeadDim;
     const int b = m / p.T, t = m - b * p.T;
-    const int nn = n < D ? n : n - D;
+    const int seg = n / D, nn = n - seg * D;          // 0: q, 1: k, 2: v (merged QKV projection)
     const int h = nn / kHeadDim, d = nn - h * kHeadDim;
     const long idx = (((long)b * p.H + h) * p.T + t) * kHeadDim + d;
     const float v = acc + p.bias[n];
-    if (n < D) {
+    if (seg == 0) {
       put<TOp>(p.qu, idx, v + p.pos_u[nn], p.round_out != 0);
       put<TOp>(p.qv, idx, v + p.pos_v[nn], p.round_out != 0);
     } else {
-      put<TOp>(p.kk, idx, v, p.round_out != 0);
+      put<TOp>(seg == 1 ? p.kk : p.vt, idx, v, p.round_out != 0);
     }
   } else if constexpr (MODE == EPI_VT) {
     const int b = n / p.T, t = n - b * p.T;
@@ -261,8 +262,8 @@ int attention_simt(const float* qu, const float* qv, const float* kk, const floa
 int attention_tc(const float* qu, const float* qv, const float* kk, const float* vt, const float* pos,
                  const int32_t* lengths, float* ctx, int B, int T, int H, int Tp, int Rp, int round_out,
                  cudaStream_t st);
-// fp16 operands (attention_f16.cu): same layouts with __half elements, Tp a multiple of 8; ctx stored as __half
-int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vt, const __half* pos,
-                  const int32_t* lengths, __half* ctx, int B, int T, int H, int Tp, int Rp, cudaStream_t st);
+// fp16 operands (attention_f16.cu): qu, qv, kk, vv all (B,H,T,64) __half (V in its natural layout); ctx __half
+int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vv, const __half* pos,
+                  const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st);
 
 }  // namespace avsr

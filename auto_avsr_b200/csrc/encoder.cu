@@ -55,7 +55,8 @@ static Prepared layout_prepared(const AvsrEncoderConfig& c, void* base) {
   for (auto& L : P.layers) {
     L.ffm_w1 = cv.take(F * D); L.ffm_b1 = cv.take(F); L.ffm_w2 = cv.take(D * F); L.ffm_b2 = cv.take(D);
     L.ln_ffm_w = cv.take(D); L.ln_ffm_b = cv.take(D);
-    L.qk_w = cv.take(2 * D * D); L.qk_b = cv.take(2 * D); L.v_w = cv.take(D * D); L.v_b = cv.take(D);
+    L.qk_w = cv.take(3 * D * D); L.qk_b = cv.take(3 * D);   // q | k | v rows contiguous (one QKV GEMM in F16 mode)
+    L.v_w = nullptr; L.v_b = L.qk_b + 2 * D;                // v_w is an operand-sized offset into qk_w (see v_weights())
     L.out_w = cv.take(D * D); L.out_b = cv.take(D); L.pos_u = cv.take(D); L.pos_v = cv.take(D);
     L.ln_mha_w = cv.take(D); L.ln_mha_b = cv.take(D);
     L.pw1_w = cv.take(2 * D * D); L.pw1_b = cv.take(2 * D); L.dw_wt = cv.take(K * D);
@@ -204,7 +205,9 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = opr;
     AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, st));
   }
-  if (W.Tp != T) AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
+  // v^T pad columns [T, Tp) must be finite (FP32 / TF32 paths; the F16 path keeps V un-transposed)
+  if (W.Tp != T && prec != AVSR_PREC_F16)
+    AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
 
   for (int l = 0; l < L; ++l) {
     const LayerPrep& w = P.layers[l];
@@ -223,18 +226,25 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st));
     {
       EpiParams e{};
-      e.M = N; e.N = 2 * D; e.bias = w.qk_b; e.T = T; e.H = H; e.pos_u = w.pos_u; e.pos_v = w.pos_v;
-      e.qu = W.qu; e.qv = W.qv; e.kk = W.kk; e.round_out = opr;
-      AVSR_TRY(run_gemm(prec, EPI_QK, W.xn, w.qk_w, N, 2 * D, D, e, st));
-      EpiParams v{};
-      v.M = D; v.N = N; v.bias = w.v_b; v.T = T; v.H = H; v.Tp = W.Tp; v.vt = W.vt; v.round_out = opr;
-      AVSR_TRY(run_gemm(prec, EPI_VT, w.v_w, W.xn, D, N, D, v, st));
+      e.M = N; e.bias = w.qk_b; e.T = T; e.H = H; e.pos_u = w.pos_u; e.pos_v = w.pos_v;
+      e.qu = W.qu; e.qv = W.qv; e.kk = W.kk; e.vt = W.vt; e.round_out = opr;
+      if (prec == AVSR_PREC_F16) {
+        // one QKV projection; V keeps the (B,H,T,64) layout (the P.V MMA reads it as an MN-major operand)
+        e.N = 3 * D;
+        AVSR_TRY(run_gemm(prec, EPI_QK, W.xn, w.qk_w, N, 3 * D, D, e, st));
+      } else {
+        e.N = 2 * D;
+        AVSR_TRY(run_gemm(prec, EPI_QK, W.xn, w.qk_w, N, 2 * D, D, e, st));
+        EpiParams v{};
+        v.M = D; v.N = N; v.bias = w.v_b; v.T = T; v.H = H; v.Tp = W.Tp; v.vt = W.vt; v.round_out = opr;
+        AVSR_TRY(run_gemm(prec, EPI_VT, op_offset(w.qk_w, (size_t)2 * D * D, prec), W.xn, D, N, D, v, st));
+      }
     }
     {
       const void* pos_l = op_offset(W.pos, (size_t)l * H * W.Rp * kHeadDim, prec);
       if (prec == AVSR_PREC_F16)
         AVSR_TRY(attention_f16((const __half*)W.qu, (const __half*)W.qv, (const __half*)W.kk, (const __half*)W.vt,
-                               (const __half*)pos_l, lengths, (__half*)W.ctx, B, T, H, W.Tp, W.Rp, st));
+                               (const __half*)pos_l, lengths, (__half*)W.ctx, B, T, H, W.Rp, st));
       else if (prec == AVSR_PREC_TF32)
         AVSR_TRY(attention_tc(W.qu, W.qv, W.kk, W.vt, (const float*)pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, 1, st));
       else
@@ -342,7 +352,8 @@ int avsr_prepare_weights(const AvsrEncoderConfig* cfg, const AvsrLayerParams* la
     AVSR_TRY(copy_round(s.norm_ffm_w, d.ln_ffm_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_ffm_b, d.ln_ffm_b, D, 0, st));
     AVSR_TRY(copy_round(s.q_w, d.qk_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.k_w, op_offset(d.qk_w, (size_t)D * D, precision), D * D, rnd, st));
     AVSR_TRY(copy_round(s.q_b, d.qk_b, D, 0, st)); AVSR_TRY(copy_round(s.k_b, d.qk_b + D, D, 0, st));
-    AVSR_TRY(copy_round(s.v_w, d.v_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.v_b, d.v_b, D, 0, st));
+    AVSR_TRY(copy_round(s.v_w, op_offset(d.qk_w, (size_t)2 * D * D, precision), D * D, rnd, st));
+    AVSR_TRY(copy_round(s.v_b, d.qk_b + 2 * D, D, 0, st));
     AVSR_TRY(copy_round(s.out_w, d.out_w, D * D, rnd, st)); AVSR_TRY(copy_round(s.out_b, d.out_b, D, 0, st));
     AVSR_TRY(copy_round(s.pos_bias_u, d.pos_u, D, 0, st)); AVSR_TRY(copy_round(s.pos_bias_v, d.pos_v, D, 0, st));
     AVSR_TRY(copy_round(s.norm_mha_w, d.ln_mha_w, D, 0, st)); AVSR_TRY(copy_round(s.norm_mha_b, d.ln_mha_b, D, 0, st));
@@ -550,11 +561,12 @@ int avsr_relpos_attention(const float* q, const float* k, const float* v, const 
   split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_u, qu, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
   split_heads_kernel<<<blocks, 256, 0, st>>>(q, pos_bias_v, qv, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
   split_heads_kernel<<<blocks, 256, 0, st>>>(k, nullptr, kk, B, T, H, Tp, 0, kind); AVSR_CHECK_LAUNCH();
-  split_heads_kernel<<<blocks, 256, 0, st>>>(v, nullptr, vt, B, T, H, Tp, 1, kind); AVSR_CHECK_LAUNCH();
+  split_heads_kernel<<<blocks, 256, 0, st>>>(v, nullptr, vt, B, T, H, Tp, precision == AVSR_PREC_F16 ? 0 : 1, kind);
+  AVSR_CHECK_LAUNCH();
   split_heads_kernel<<<blocks, 256, 0, st>>>(p, nullptr, pos, 1, R, H, R, 0, kind); AVSR_CHECK_LAUNCH();
   if (precision == AVSR_PREC_F16) {
     AVSR_TRY(attention_f16((const __half*)qu, (const __half*)qv, (const __half*)kk, (const __half*)vt, (const __half*)pos,
-                           lengths, (__half*)ctxh, B, T, H, Tp, R, st));
+                           lengths, (__half*)ctxh, B, T, H, R, st));
     half_to_float_kernel<<<blocks, 256, 0, st>>>((const __half*)ctxh, ctx, (long)N * D);
     AVSR_CHECK_LAUNCH();
     return AVSR_OK;

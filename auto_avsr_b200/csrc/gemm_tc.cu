@@ -144,7 +144,7 @@ __device__ __forceinline__ void emit_heads(const EpiParams& p, void* base, int m
   if (m >= p.M || n >= p.N) return;
   const int D = p.H * kHeadDim;
   const int b = m / p.T, t = m - b * p.T;
-  const int nn = n < D ? n : n - D;
+  const int nn = n % D;                              // q | k | v segments share the head-major layout
   const int h = nn >> 6, d0 = nn & 63;
   *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(base) + (((long)b * p.H + h) * p.T + t) * kHeadDim + d0) = pay;
 }
@@ -492,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                emit_heads<TOp>(ep, ep.kk, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+                emit_heads<TOp>(ep, n < 2 * D ? ep.kk : ep.vt, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
               __syncwarp();
             }
           } else {

@@ -141,6 +141,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16, A K-major, B MN-major (bit 16): B tile stored [k rows][N contiguous], e.g. V (keys x d_k) for P.V
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(int M, int N) {
+  return umma_idesc_f16(M, N) | (1u << 16);
+}
+
 }  // namespace sm100
 
 // host: 2-D row-major tensor (rows x cols, row stride ld elements of esz = 4 (fp32) or 2 (fp16) bytes) -> TMA map with a
