@@ -64,7 +64,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   float* xch = reinterpret_cast<float*>(gen + AH_XCH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * AH_BQ, h = blockIdx.y, b = blockIdx.z;
+  // grid = (H, B, query tiles): the query tile is the SLOWEST block index, so the last tile of every utterance
+  // (mostly rows >= T, e.g. 16 valid of 128 at T = 400) is scheduled in the final, partially filled wave
+  const int h = blockIdx.x, b = blockIdx.y, i0 = blockIdx.z * AH_BQ;
   const int bh = b * H + h;
   pdl_launch_dependents();
   int L = T;
@@ -155,6 +157,14 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = gen + AH_P + hf * (AH_BQ * 128) + r * 128;
+    if (i0 + q * 32 >= T) {
+      // all 32 query rows of this warp lie beyond T (last query tile): nothing to compute or store -- only keep the
+      // barrier protocol going (its P rows / accumulator rows are never read by anyone)
+      for (int it = 0; it < nkt; ++it) {
+        mbar_arrive(p_full);
+        mbar_wait(o_full, it & 1);
+      }
+    } else {
 
     for (int it = 0; it < nkt; ++it) {
       const int j0 = it * AH_BKV + hf * 64;       // first key this thread scores
@@ -255,6 +265,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
 #pragma unroll
       for (int d = 0; d < 32; d += 4) store_op4<__half>(dst + d, o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
     }
+    }  // valid warp
   }
   tc_fence_before();
   __syncthreads();
@@ -280,7 +291,7 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
     AVSR_CUDA_TRY(cudaFuncSetAttribute(attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AH_SMEM));
     attr_done = true;
   }
-  dim3 grid(cdiv(T, AH_BQ), H, B);
+  dim3 grid(H, B, cdiv(T, AH_BQ));
   AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
   return AVSR_OK;
 }

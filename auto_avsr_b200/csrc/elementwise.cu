@@ -229,29 +229,59 @@ int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st) {
 // y[b,t,c] = silu( (sum_k wt[k][c] * x[b, t+k-half, c]) * scale[c] + shift[c] ),  x zero outside [0,T) per
 // utterance row b -- no length mask: padded frames are data (conformer_encoder.py:30-35).
 // scale/shift fold the depthwise bias and the BatchNorm running statistics (avsr_prepare_weights).
-// Tile: 64 channels x 32 frames per CTA; the (32+K-1) x 64 input patch and the K x 64 taps are staged in
-// shared memory with coalesced float4 loads; each thread produces 2 frames of one channel quad.
-constexpr int kDwCh = 64;
-constexpr int kDwTT = 32;
+// Tile: 64 channels x 64 frames per CTA (128 threads); the (64+K-1) x 64 input patch and the K x 64 taps are staged
+// in shared memory with coalesced float4 loads along the channel axis.  Each thread produces 8 consecutive frames of
+// one channel quad with a register sliding window: per tap ONE new input row and one tap vector are read from
+// shared memory for 8 outputs (the v1 kernel read 2 per output pair: 4x more shared-memory traffic, r01 profile).
+constexpr int kDwCh = 64;    // channels per CTA (16 quads)
+constexpr int kDwTT = 64;    // frames per CTA
+constexpr int kDwFr = 8;     // frames per thread
+constexpr int kDwThreads = (kDwCh / 4) * (kDwTT / kDwFr);   // 128
 
-__global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt,
-                                                             const float* __restrict__ scale,
-                                                             const float* __restrict__ shift, void* __restrict__ y,
-                                                             int T, int C, int K, int out_kind) {
+template <int K>
+__device__ __forceinline__ void dw_accumulate(const float4* in_s, const float4* w_s, int q, int ts, int k_runtime,
+                                              float4 (&acc)[kDwFr]) {
+  // K > 0: fully unrolled (window shifts become register renames); K == 0: runtime tap count
+  constexpr int KK = K > 0 ? K : 1;
+  float4 win[kDwFr];
+#pragma unroll
+  for (int j = 0; j < kDwFr - 1; ++j) win[j + 1] = in_s[(ts * kDwFr + j) * 16 + q];
+  const int taps = K > 0 ? KK : k_runtime;
+#pragma unroll
+  for (int k = 0; k < (K > 0 ? KK : 256); ++k) {
+    if (K == 0 && k >= taps) break;
+#pragma unroll
+    for (int j = 0; j < kDwFr - 1; ++j) win[j] = win[j + 1];
+    win[kDwFr - 1] = in_s[(ts * kDwFr + kDwFr - 1 + k) * 16 + q];
+    const float4 w = w_s[k * 16 + q];
+#pragma unroll
+    for (int j = 0; j < kDwFr; ++j) {
+      acc[j].x = fmaf(w.x, win[j].x, acc[j].x); acc[j].y = fmaf(w.y, win[j].y, acc[j].y);
+      acc[j].z = fmaf(w.z, win[j].z, acc[j].z); acc[j].w = fmaf(w.w, win[j].w, acc[j].w);
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift, void* __restrict__ y,
+                                                                    int T, int C, int k_runtime, int out_kind) {
   extern __shared__ float4 dw_smem[];
   pdl_launch_dependents();
-  const int rows_in = kDwTT + K - 1;
+  const int Kt = K > 0 ? K : k_runtime;
+  const int rows_in = kDwTT + Kt - 1;
   float4* in_s = dw_smem;                          // [rows_in][16]
   float4* w_s = dw_smem + rows_in * (kDwCh / 4);   // [K][16]
   const int c0 = blockIdx.x * kDwCh;
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
-  const int half = (K - 1) >> 1;
+  const int half = (Kt - 1) >> 1;
   const int tid = threadIdx.x;
   const float* xb = x + (long)b * T * C;
 
   // the taps are parameters: stage them before waiting on the producer of x
-  for (int i = tid; i < K * (kDwCh / 4); i += 256) {
+  for (int i = tid; i < Kt * (kDwCh / 4); i += kDwThreads) {
     const int k = i >> 4, q = i & 15;
     const int c = c0 + q * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -259,7 +289,7 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __rest
     w_s[i] = v;
   }
   pdl_wait();
-  for (int i = tid; i < rows_in * (kDwCh / 4); i += 256) {
+  for (int i = tid; i < rows_in * (kDwCh / 4); i += kDwThreads) {
     const int r = i >> 4, q = i & 15;
     const int t = t0 - half + r, c = c0 + q * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -268,28 +298,25 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const float* __rest
   }
   __syncthreads();
 
-  const int q = tid & 15, ts = tid >> 4;
+  const int q = tid & 15, ts = tid >> 4;           // channel quad, group of 8 frames
   const int c = c0 + q * 4;
   if (c >= C) return;
+  float4 acc[kDwFr];
+#pragma unroll
+  for (int j = 0; j < kDwFr; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  dw_accumulate<K>(in_s, w_s, q, ts, k_runtime, acc);
   const float4 sc = *reinterpret_cast<const float4*>(scale + c);
   const float4 sh = *reinterpret_cast<const float4*>(shift + c);
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-  for (int k = 0; k < K; ++k) {
-    const float4 w = w_s[k * 16 + q];
-    const float4 u0 = in_s[(ts + k) * 16 + q];
-    const float4 u1 = in_s[(ts + 16 + k) * 16 + q];
-    a0.x = fmaf(w.x, u0.x, a0.x); a0.y = fmaf(w.y, u0.y, a0.y); a0.z = fmaf(w.z, u0.z, a0.z); a0.w = fmaf(w.w, u0.w, a0.w);
-    a1.x = fmaf(w.x, u1.x, a1.x); a1.y = fmaf(w.y, u1.y, a1.y); a1.z = fmaf(w.z, u1.z, a1.z); a1.w = fmaf(w.w, u1.w, a1.w);
-  }
-  auto finish = [&](float4 a, int t) {
-    if (t >= T) return;
+#pragma unroll
+  for (int j = 0; j < kDwFr; ++j) {
+    const int t = t0 + ts * kDwFr + j;
+    if (t >= T) break;
     float4 o;
-    o.x = fmaf(a.x, sc.x, sh.x); o.y = fmaf(a.y, sc.y, sh.y); o.z = fmaf(a.z, sc.z, sh.z); o.w = fmaf(a.w, sc.w, sh.w);
+    o.x = fmaf(acc[j].x, sc.x, sh.x); o.y = fmaf(acc[j].y, sc.y, sh.y);
+    o.z = fmaf(acc[j].z, sc.z, sh.z); o.w = fmaf(acc[j].w, sc.w, sh.w);
     o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
     store_kind4(y, ((long)b * T + t) * C + c, out_kind, o.x, o.y, o.z, o.w);
-  };
-  finish(a0, t0 + ts);
-  finish(a1, t0 + ts + 16);
+  }
 }
 
 int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, void* y, int B,
@@ -297,10 +324,14 @@ int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, c
   AVSR_REQUIRE(C % 4 == 0 && K % 2 == 1 && K >= 1 && K <= 255, "dwconv: C=%d must be a multiple of 4, K=%d odd", C, K);
   if (B <= 0 || T <= 0) return AVSR_OK;
   const size_t smem = (size_t)(kDwTT + K - 1 + K) * (kDwCh / 4) * sizeof(float4);
-  if (smem > 48 * 1024)
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(C, kDwCh), cdiv(T, kDwTT), B);
-  AVSR_LAUNCH(dwconv_bn_silu_kernel, grid, 256, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
+  if (K == 31) {   // the reference's cnn_module_kernel (e2e_asr_conformer.py:38): fully unrolled taps
+    AVSR_LAUNCH(dwconv_bn_silu_kernel<31>, grid, kDwThreads, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
+  } else {
+    if (smem > 48 * 1024)
+      AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AVSR_LAUNCH(dwconv_bn_silu_kernel<0>, grid, kDwThreads, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
+  }
   return AVSR_OK;
 }
 
