@@ -48,6 +48,8 @@ extern std::atomic<uint64_t> g_launches;
     if (_r != AVSR_OK) return _r; \
   } while (0)
 
+constexpr int kSplitCounters = 4096;  // split-K tile counters a caller must provide (EpiParams::counters)
+constexpr int kMaxSplits = 8;         // split-K slices gemm_tc may choose; sizes EpiParams::partial
 constexpr int kHeadDim = 64;  // d_k of the reference encoder (768 / 12); the attention kernels are built for it
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -180,6 +182,8 @@ struct EpiParams {
   int T, H, Tp, Rp;   // frames per utterance, heads, padded T of v^T, padded rows of the pos table
   const float* pos_u; // QK: [H*64]
   const float* pos_v;
+  float* partial;     // split-K: fp32 workspace [splits][M][ldo] for the partial tiles (deterministic fix-up)
+  int* counters;      // split-K: one arrival counter per output tile, zero on entry, reset by the last arriver
   void* qu;           // operand-typed (float for OP_F32/OP_TF32, __half for OP_F16)
   void* qv;
   void* kk;

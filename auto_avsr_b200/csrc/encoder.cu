@@ -147,6 +147,8 @@ static inline const void* op_offset(const void* base, size_t elems, int precisio
 // ------------------------------------------------------------------ workspace
 struct Workspace {
   float *x, *xn, *hid, *qu, *qv, *kk, *vt, *ctx, *glu, *dw, *pe, *pos;
+  float* splitk;      // [kMaxSplits][N][d_model] fp32 partial tiles of the split-K residual GEMMs
+  int* counters;      // [kSplitCounters] tile arrival counters (zero between launches)
   int32_t* lengths;
   int Tp, Rp;
   size_t bytes;
@@ -164,6 +166,8 @@ static Workspace layout_workspace(const AvsrEncoderConfig& c, int B, int T, void
   W.ctx = cv.take(N * D); W.glu = cv.take(N * D); W.dw = cv.take(N * D);
   W.pe = cv.take((size_t)W.Rp * D);
   W.pos = cv.take((size_t)c.num_blocks * W.Rp * D);
+  W.splitk = cv.take((size_t)kMaxSplits * N * D);
+  W.counters = reinterpret_cast<int*>(cv.take((size_t)kSplitCounters));
   W.lengths = reinterpret_cast<int32_t*>(cv.take((size_t)B));
   W.bytes = cv.off;
   return W;
@@ -183,6 +187,14 @@ static EpiParams epi_linear(int M, int N, const float* bias, void* out, const fl
   return e;
 }
 
+// residual-stream GEMM: x += alpha * (A W^T + b); may be split along K (deterministic fix-up through `W.splitk`)
+static EpiParams epi_resid(int M, int N, const float* bias, float* x, float alpha, float* splitk, int* counters) {
+  EpiParams e = epi_linear(M, N, bias, x, x, alpha, 0, 0);
+  e.partial = splitk;
+  e.counters = counters;
+  return e;
+}
+
 static int run_gemm(int prec, int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& e,
                     cudaStream_t st) {
   if (prec == AVSR_PREC_FP32)
@@ -198,6 +210,8 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
   const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
   const size_t stage_bytes = (size_t)N * D * sizeof(float);
 
+  // split-K tile counters must be zero on entry (they re-arm themselves; this covers a first use / an aborted run)
+  AVSR_CUDA_TRY(cudaMemsetAsync(W.counters, 0, kSplitCounters * sizeof(int), st));
   // pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
   AVSR_TRY(launch_sinusoid(W.pe, T, D, opk, st));
   {
@@ -220,7 +234,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     // (for l > 0 the norm_ff_macaron output was produced together with the previous layer's norm_final)
     if (l == 0) AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, opr), st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_linear(N, D, w.ffm_b2, W.x, W.x, 0.5f, 0, 0), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_resid(N, D, w.ffm_b2, W.x, 0.5f, W.splitk, W.counters), st));
     AVSR_TRY(tap(0));
     // (2) rel-pos MHA: x += out(attn(LN(x)))                                  conformer_encoder.py:119-142
     AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st));
@@ -250,7 +264,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       else
         AVSR_TRY(attention_simt(W.qu, W.qv, W.kk, W.vt, (const float*)pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, 0, st));
     }
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.ctx, w.out_w, N, D, D, epi_linear(N, D, w.out_b, W.x, W.x, 1.0f, 0, 0), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.ctx, w.out_w, N, D, D, epi_resid(N, D, w.out_b, W.x, 1.0f, W.splitk, W.counters), st));
     AVSR_TRY(tap(1));
     // (3) conv module: x += pw2(silu(bn(dw(glu(pw1 LN(x))))))                 conformer_encoder.py:145-151, :30-35
     AVSR_TRY(launch_layernorm(W.x, w.ln_conv_w, w.ln_conv_b, W.xn, N, D, opk, st));
@@ -260,12 +274,12 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       AVSR_TRY(run_gemm(prec, EPI_GLU, W.xn, w.pw1_w, N, 2 * D, D, e, st));
     }
     AVSR_TRY(launch_dwconv_bn_silu(W.glu, w.dw_wt, w.dw_scale, w.dw_shift, W.dw, B, T, D, c.cnn_kernel, opk, st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.dw, w.pw2_w, N, D, D, epi_linear(N, D, w.pw2_b, W.x, W.x, 1.0f, 0, 0), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.dw, w.pw2_w, N, D, D, epi_resid(N, D, w.pw2_b, W.x, 1.0f, W.splitk, W.counters), st));
     AVSR_TRY(tap(2));
     // (4) FFN: x += 0.5 * w2(relu(w1 LN(x)))                                  conformer_encoder.py:154-159
     AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, opr), st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_linear(N, D, w.ff_b2, W.x, W.x, 0.5f, 0, 0), st));
+    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_resid(N, D, w.ff_b2, W.x, 0.5f, W.splitk, W.counters), st));
     AVSR_TRY(tap(3));
     // (5) x = LN_final(x)                                                     conformer_encoder.py:161-162
     //     fused with the next layer's norm_ff_macaron: one pass writes x (fp32) and xn (operand)
