@@ -720,6 +720,11 @@ int gemm_tc(int mode, int opk, const void* A, const void* Bw, int M, int N, int 
   const int ke = opk == OP_F16 ? 64 : 32;
   AVSR_REQUIRE(K >= ke && K % ke == 0, "gemm_tc: K=%d must be a multiple of %d", K, ke);
   if (M <= 0 || N <= 0) return AVSR_OK;
+  if (opk == OP_F16 && mode == EPI_LINEAR) {      // FFN-shaped problems: CTA-pair kernel (half the bytes per MAC per SM)
+    int handled = 0;
+    AVSR_TRY(gemm_tc2_try(A, Bw, M, N, K, ep, st, &handled));
+    if (handled) return AVSR_OK;
+  }
   if (opk == OP_F16) return dispatch_mode<__half>(mode, A, Bw, M, N, K, ep, st);
   return dispatch_mode<float>(mode, A, Bw, M, N, K, ep, st);
 }

@@ -1,0 +1,310 @@
+// Two-SM tensor-core GEMM (tcgen05 cta_group::2) for the FFN projections: y = [resid + alpha *] act(x W^T + b).
+//
+// Why: the r01 profiles show the 1-CTA kernel's main loop is bound by what one SM can ingest through TMA
+// (~46 B/cycle), not by the tensor pipe.  A CTA PAIR (thread-block cluster of 2 on one TPC) computes a 256 x BNP
+// tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader CTA: each CTA stages only its own 128 rows of
+// A and HALF of the B rows (the MMA reads the other half from the peer's shared memory), so per SM the bytes per
+// MAC halve compared with a 128 x 128 tile and the tensor pipe stays ~balanced with the ingest port
+// (FFN w_1, pair tile 256 x 512: 48 KB per k-block per SM = 1043 cycles of ingest vs 1024 cycles of MMA).
+//
+// Structure per CTA (320 threads): warp 0 TMA producer (both CTAs; 2-SM TMA signals the LEADER's `full` barrier),
+// warp 1 MMA issuer (leader only) + TMEM allocation (both, cta_group::2), warps 2-9 epilogue (both; each CTA drains
+// the 128 accumulator rows that live in its own TMEM through the same staged, coalesced epilogue as gemm_tc.cu).
+// One pair-tile per cluster (the FFN shapes give 42 pair-tiles <= 74 pairs), so no accumulator double buffering.
+// fp16 operands, EPI_LINEAR only; everything else uses gemm_tc.cu.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace avsr {
+
+using namespace sm100;
+
+constexpr int T2_THREADS = 320;
+constexpr int T2_STG_ROW = 144;
+constexpr int T2_STG_WARP = 32 * T2_STG_ROW;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address with the CTA-pair peer bit cleared = leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {  // one warp in EACH CTA of the pair, same dst offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's shared memory, completion bytes are credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[256 rows: 128 per CTA] * B[N: N/2 rows per CTA]^T, issued by the leader CTA only
+__device__ __forceinline__ void mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far -> arrive on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BNP>
+struct T2Cfg {
+  static constexpr int kNSub = BNP > 256 ? BNP / 256 : 1;       // MMAs per k-step (UMMA N <= 256)
+  static constexpr int kUmmaN = BNP / kNSub;                    // 128 or 256
+  static constexpr int kBRows = kUmmaN / 2;                     // B rows per CTA per sub-block
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = kNSub * kBRows * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;         // per CTA
+  static constexpr int kVecBytes = BNP * 4;
+  static constexpr int kFixed = 1024 + 256 + kVecBytes + 8 * T2_STG_WARP;
+  static constexpr int kStagesFit = (222 * 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmem = kStages * kStageBytes + kFixed;
+  static constexpr int kTmemCols = BNP < 32 ? 32 : BNP;
+  static_assert(kStages >= 2 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "bad pair tile");
+};
+
+// lane-per-row staging writes / transposed reads (same scheme as gemm_tc.cu)
+__device__ __forceinline__ void t2_stage_f32(uint8_t* stg, int lane, const float* o) {
+  uint8_t* row = stg + lane * T2_STG_ROW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row + 16 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+__device__ __forceinline__ void t2_stage_f16(uint8_t* stg, int lane, const float* o) {
+  uint8_t* row = stg + lane * T2_STG_ROW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 t;
+    __half2 h0 = __halves2half2(to_half_sat(o[8 * j]), to_half_sat(o[8 * j + 1]));
+    __half2 h1 = __halves2half2(to_half_sat(o[8 * j + 2]), to_half_sat(o[8 * j + 3]));
+    __half2 h2 = __halves2half2(to_half_sat(o[8 * j + 4]), to_half_sat(o[8 * j + 5]));
+    __half2 h3 = __halves2half2(to_half_sat(o[8 * j + 6]), to_half_sat(o[8 * j + 7]));
+    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(row + 16 * j) = t;
+  }
+}
+__device__ __forceinline__ uint4 t2_stage_read(const uint8_t* stg, int it, int lane) {
+  return *reinterpret_cast<const uint4*>(stg + (it * 4 + (lane >> 3)) * T2_STG_ROW + (lane & 7) * 16);
+}
+
+template <int BNP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_n,
+                EpiParams ep) {
+  using Cfg = T2Cfg<BNP>;
+  constexpr int S = Cfg::kStages;
+  constexpr int KE = 64;   // halves per 128-byte k-block
+  extern __shared__ uint8_t t2_smem_raw[];
+  const uint32_t raw = smem_u32(t2_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = t2_smem_raw + (base - raw);
+  const uint32_t bars = base + S * Cfg::kStageBytes;   // full[S], empty[S], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * Cfg::kStageBytes + (2 * S + 1) * 8);
+  float* s_bias = reinterpret_cast<float*>(gen + S * Cfg::kStageBytes + 256);
+  uint8_t* stg_base = gen + S * Cfg::kStageBytes + 256 + Cfg::kVecBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * S);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int m0 = (pair / tiles_n) * 256, n0 = (pair % tiles_n) * BNP;
+  const int nkb = K / KE;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised and TMEM is allocated before anyone signals a peer
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);                                  // own stage free (leader's commit, multicast)
+        if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes); // bytes of BOTH CTAs land on the leader's barrier
+        const uint32_t dst = base + s * Cfg::kStageBytes;
+        tma_load_2d_2sm(dst, &tmA, kb * KE, m0 + (int)rank * 128, full_bar(s));
+#pragma unroll
+        for (int j = 0; j < Cfg::kNSub; ++j)
+          tma_load_2d_2sm(dst + Cfg::kABytes + j * (Cfg::kBRows * 128), &tmB, kb * KE,
+                          n0 + j * Cfg::kUmmaN + (int)rank * Cfg::kBRows, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(256, Cfg::kUmmaN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = base + s * Cfg::kStageBytes;
+        const uint64_t a_desc = umma_desc_sw128(a_addr);
+#pragma unroll
+        for (int j = 0; j < Cfg::kNSub; ++j) {
+          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + j * (Cfg::kBRows * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_f16_2sm(tmem_base + j * Cfg::kUmmaN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        }
+        tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
+      }
+      tc_commit_2sm(tmem_full_bar);        // accumulator complete: wakes both CTAs' epilogues
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (both CTAs: own 128 rows)
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    uint8_t* stg = stg_base + (warp - 2) * T2_STG_WARP;
+    const int cb = chalf * (BNP / 2), ce = cb + BNP / 2;
+    const int pr = lane >> 3, pc = lane & 7;
+    for (int c = threadIdx.x - 64; c < BNP; c += T2_THREADS - 64) {
+      const int n = n0 + c;
+      s_bias[c] = (ep.bias && n < ep.N) ? ep.bias[n] : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int mw = m0 + (int)rank * 128 + q * 32;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (!ep.round_out) {                                   // fp32 destination (+ residual)
+#pragma unroll 1
+      for (int c = cb; c < ce; c += 32) {
+        float v[32];
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        const float* sb = s_bias + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+        t2_stage_f32(stg, lane, v);
+        __syncwarp();
+        const int n = n0 + c + pc * 4;
+        float4 r[8];
+        if (ep.resid) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = mw + it * 4 + pr;
+            r[it] = (m < ep.M && n < ep.N) ? *reinterpret_cast<const float4*>(ep.resid + (long)m * ep.ldo + n)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = mw + it * 4 + pr;
+          const uint4 pay = t2_stage_read(stg, it, lane);
+          float4 o = *reinterpret_cast<const float4*>(&pay);
+          if (ep.resid) {
+            o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
+            o.z = r[it].z + ep.alpha * o.z; o.w = r[it].w + ep.alpha * o.w;
+          }
+          if (m < ep.M && n < ep.N) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long)m * ep.ldo + n) = o;
+        }
+        __syncwarp();
+      }
+    } else {                                               // fp16 operand destination (FFN hidden)
+#pragma unroll 1
+      for (int c = cb; c < ce; c += 64) {
+        float v[64];
+        tmem_ld32(trow + c, v);
+        tmem_ld32(trow + c + 32, v + 32);
+        tmem_ld_wait();
+        const float* sb = s_bias + c;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+        t2_stage_f16(stg, lane, v);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = mw + it * 4 + pr, n = n0 + c + pc * 8;
+          const uint4 pay = t2_stage_read(stg, it, lane);
+          if (m < ep.M && n < ep.N) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + (long)m * ep.ldo + n) = pay;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still be reading TMEM / its barriers may still receive our commits
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BNP>
+static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  using Cfg = T2Cfg<BNP>;
+  CUtensorMap tmA, tmB;
+  AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 2));
+  AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kBRows, 2));
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSR_CUDA_TRY(cudaFuncSetAttribute(gemm_tc2_kernel<BNP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_done = true;
+  }
+  const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
+  AVSR_LAUNCH(gemm_tc2_kernel<BNP>, 2 * tiles_m * tiles_n, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
+  return AVSR_OK;
+}
+
+// Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.
+int gemm_tc2_try(const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int* handled) {
+  *handled = 0;
+  static const bool enabled = [] { const char* e = getenv("AVSR_B200_2CTA"); return !(e && e[0] == '0'); }();
+  if (!enabled || K % 64 != 0 || N % 8 != 0 || M < 256) return AVSR_OK;
+  if ((ep.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(ep.out) & 15) || (reinterpret_cast<uintptr_t>(ep.resid) & 15))
+    return AVSR_OK;
+  // Pair-tile width: per-SM ingest ~ (128 + BNP/2) * K * 2 bytes shrinks with BNP, so take the NARROWEST width whose
+  // pair-tiles still fit one wave of 74 clusters (a second wave would double the time of this one-tile-per-cluster
+  // kernel): FFN w_1 (N = 3072) -> 512 (42 pairs), FFN w_2 / out / pw2 (N = 768) -> 128 (42 pairs).
+  const int tiles_m = cdiv(M, 256);
+  int bnp = 0;
+  for (int cand : {128, 256, 512}) {
+    if (N % cand == 0 && tiles_m * (N / cand) <= 74) { bnp = cand; break; }
+  }
+  if (!bnp) return AVSR_OK;
+  *handled = 1;
+  const __half* a = reinterpret_cast<const __half*>(A);
+  const __half* b = reinterpret_cast<const __half*>(Bw);
+  if (bnp == 512) return launch_tc2<512>(a, b, M, N, K, ep, st);
+  if (bnp == 256) return launch_tc2<256>(a, b, M, N, K, ep, st);
+  return launch_tc2<128>(a, b, M, N, K, ep, st);
+}
+
+}  // namespace avsr
