@@ -237,7 +237,9 @@ def kernel_roofline(dev, peaks, precision):
         except Exception:
             traffic = None
     kind = "kind::f16, fp16 operands" if precision == "f16" else "kind::tf32"
-    out = {"bound": "tensor", "kernel": f"gemm_tc_kernel<EPI_LINEAR> FFN w_1 1600x3072x768 (tcgen05 {kind}, fp32 accumulate)",
+    kname = ("gemm_tc2_kernel<512> (cta_group::2 pair tile 256x512)" if precision == "f16"
+             else "gemm_tc_kernel<EPI_LINEAR> (persistent, 1-CTA)")
+    out = {"bound": "tensor", "kernel": f"{kname} FFN w_1 1600x3072x768 (tcgen05 {kind}, fp32 accumulate)",
            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks['source']}, cuBLAS bf16 8192^3 burst)",
            "us_per_launch": per_launch_s * 1e6, "algorithmic_flops_per_launch": flops, "traffic": traffic}
