@@ -286,11 +286,7 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
   AVSR_TRY(make_tmap_2d(&tmK, kk, rows, 64, 64, AH_BKV, 2));
   AVSR_TRY(make_tmap_2d(&tmV, vv, rows, 64, 64, AH_BKV, 2));
   AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AH_BAND, 2));
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AH_SMEM));
-    attr_done = true;
-  }
+  AVSR_SET_MAX_SMEM(attention_f16_kernel, AH_SMEM);
   dim3 grid(H, B, cdiv(T, AH_BQ));
   AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
   return AVSR_OK;

@@ -258,11 +258,7 @@ int attention_tc(const float* qu, const float* qv, const float* kk, const float*
   AVSR_TRY(make_tmap_2d(&tmK, kk, rows, 64, 64, AT_BKV, 4));
   AVSR_TRY(make_tmap_2d(&tmV, vt, (uint64_t)B * H * 64, (uint64_t)Tp, (uint64_t)Tp, 64, 4));
   AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AT_BAND, 4));
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_done = true;
-  }
+  AVSR_SET_MAX_SMEM(attention_tc_kernel, AT_SMEM);
   dim3 grid(cdiv(T, AT_BQ), H, B);
   AVSR_LAUNCH(attention_tc_kernel, grid, AT_THREADS, AT_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H, round_out);
   return AVSR_OK;

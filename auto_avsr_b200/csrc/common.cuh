@@ -91,6 +91,18 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return launch_kernel_impl(kernel, grid, block, smem, st, std::index_sequence_for<KArgs...>{}, std::forward<Args>(args)...);
 }
 
+// opt a kernel into > 48 KB of dynamic shared memory; remembered per device (one process may drive several GPUs)
+#define AVSR_SET_MAX_SMEM(kernel, bytes)                                                                     \
+  do {                                                                                                       \
+    static int _done_dev = -1;                                                                               \
+    int _dev = 0;                                                                                            \
+    AVSR_CUDA_TRY(cudaGetDevice(&_dev));                                                                     \
+    if (_done_dev != _dev) {                                                                                 \
+      AVSR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _done_dev = _dev;                                                                                      \
+    }                                                                                                        \
+  } while (0)
+
 #define AVSR_LAUNCH(kernel, grid, block, smem, st, ...)                                                \
   do {                                                                                                 \
     ::avsr::g_launches.fetch_add(1);                                                                   \

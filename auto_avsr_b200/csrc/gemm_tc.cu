@@ -596,12 +596,7 @@ static int launch_tc(const void* A, const void* Bw, int M, int N, int K, int spl
   CUtensorMap tmA, tmB;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, TC_BM, (int)sizeof(TOp)));
   AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN, (int)sizeof(TOp)));
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN, MSUB, TOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmem));
-    attr_done = true;
-  }
+  AVSR_SET_MAX_SMEM((gemm_tc_kernel<MODE, BN, MSUB, TOp>), Cfg::kSmem);
   const int tiles_m = cdiv(M, TC_BM * MSUB), tiles_n = cdiv(N, BN);
   if (splits > kMaxSplits || tiles_m * tiles_n > kSplitCounters) splits = 1;   // caller's workspace contract
   const int total = tiles_m * tiles_n * splits;

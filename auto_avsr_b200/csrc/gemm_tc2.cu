@@ -273,11 +273,7 @@ static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, co
   CUtensorMap tmA, tmB;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 2));
   AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kBRows, 2));
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVSR_CUDA_TRY(cudaFuncSetAttribute(gemm_tc2_kernel<BNP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_done = true;
-  }
+  AVSR_SET_MAX_SMEM(gemm_tc2_kernel<BNP>, Cfg::kSmem);
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
   AVSR_LAUNCH(gemm_tc2_kernel<BNP>, 2 * tiles_m * tiles_n, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
   return AVSR_OK;
