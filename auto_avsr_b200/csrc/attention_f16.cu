@@ -44,6 +44,14 @@ constexpr int AH_SMEM = AH_BARS + 128 + 1024;
 
 constexpr uint32_t TH_S = 0, TH_G = 128, TH_O = 384;
 
+// 2^x for x <= 0 (softmax exponents): one MUFU.EX2; results below 2^-126 flush to zero, which is what a probability
+// that small contributes anyway.  exp2f() wraps the same instruction in a denormal-range fix-up (FSETP + 2 FMUL).
+__device__ __forceinline__ float ex2_neg(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -184,26 +192,21 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         tmem_ld32(trow + TH_G + gbase + hf * 64 + c0 + 32, x + 32);
         tmem_ld32(trow + TH_S + hf * 64 + c0, s + c0);
         tmem_ld_wait();
-        // y[c] = x[c + sh], sh in [0,31]: barrel shifter, one conditional stage per bit of sh
-        if (sh & 16) {
+        // y[c] = x[c + sh], sh in [0,31]: barrel shifter, one stage per bit of sh.  Written as per-element selects
+        // (in-place is safe in increasing c: x[c + 2^k] is still the previous stage's value); the if/else form made
+        // the compiler emit divergent branches with register copies on both paths (2x the moves, r01 SASS).
+        {
+          const bool b16 = (sh & 16) != 0, b8 = (sh & 8) != 0, b4 = (sh & 4) != 0, b2 = (sh & 2) != 0, b1 = (sh & 1) != 0;
 #pragma unroll
-          for (int c = 0; c < 47; ++c) x[c] = x[c + 16];
-        }
-        if (sh & 8) {
+          for (int c = 0; c < 47; ++c) x[c] = b16 ? x[c + 16] : x[c];
 #pragma unroll
-          for (int c = 0; c < 39; ++c) x[c] = x[c + 8];
-        }
-        if (sh & 4) {
+          for (int c = 0; c < 39; ++c) x[c] = b8 ? x[c + 8] : x[c];
 #pragma unroll
-          for (int c = 0; c < 35; ++c) x[c] = x[c + 4];
-        }
-        if (sh & 2) {
+          for (int c = 0; c < 35; ++c) x[c] = b4 ? x[c + 4] : x[c];
 #pragma unroll
-          for (int c = 0; c < 33; ++c) x[c] = x[c + 2];
-        }
-        if (sh & 1) {
+          for (int c = 0; c < 33; ++c) x[c] = b2 ? x[c + 2] : x[c];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) x[c] = x[c + 1];
+          for (int c = 0; c < 32; ++c) x[c] = b1 ? x[c + 1] : x[c];
         }
         if (jc + 32 <= L) {                       // fully valid chunk: no per-key mask
 #pragma unroll
@@ -221,7 +224,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       slot[hf * 128 + r] = mloc;
       named_bar_sync(1 + q, 64);
       const float mx = fmaxf(m_run, fmaxf(mloc, slot[(hf ^ 1) * 128 + r]));   // finite: key (tile start) < L is valid
-      const float alpha = exp2f((m_run - mx) * kScale);   // first tile: exp2(-inf) = 0
+      const float alpha = ex2_neg((m_run - mx) * kScale);   // first tile: exp2(-inf) = 0
       m_run = mx;
       const float mxs = mx * kScale;
       float sum = 0.f;
@@ -232,8 +235,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(fmaf(s[8 * ch + 2 * e], kScale, -mxs));
-          const float p1 = exp2f(fmaf(s[8 * ch + 2 * e + 1], kScale, -mxs));
+          const float p0 = ex2_neg(fmaf(s[8 * ch + 2 * e], kScale, -mxs));
+          const float p1 = ex2_neg(fmaf(s[8 * ch + 2 * e + 1], kScale, -mxs));
           sum += p0 + p1;
           const __half2 hp = __floats2half2_rn(p0, p1);
           pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
