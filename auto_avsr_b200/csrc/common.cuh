@@ -117,6 +117,9 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid through ex2.approx + fast reciprocal (relative error ~1e-6: far below the 11-bit operand rounding that
+// follows in the tensor-core paths); the fp32 reference path keeps sigmoidf_acc
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -289,12 +289,24 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
     w_s[i] = v;
   }
   pdl_wait();
-  for (int i = tid; i < rows_in * (kDwCh / 4); i += kDwThreads) {
-    const int r = i >> 4, q = i & 15;
-    const int t = t0 - half + r, c = c0 + q * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T && c < C) v = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
-    in_s[i] = v;
+  {
+    const int total = rows_in * (kDwCh / 4);
+    for (int i0 = tid; i0 < total; i0 += 4 * kDwThreads) {   // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kDwThreads;
+        const int r = i >> 4, q = i & 15;
+        const int t = t0 - half + r, c = c0 + q * 4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total && t >= 0 && t < T && c < C) v[u] = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kDwThreads;
+        if (i < total) in_s[i] = v[u];
+      }
+    }
   }
   __syncthreads();
 
@@ -314,7 +326,11 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
     float4 o;
     o.x = fmaf(acc[j].x, sc.x, sh.x); o.y = fmaf(acc[j].y, sc.y, sh.y);
     o.z = fmaf(acc[j].z, sc.z, sh.z); o.w = fmaf(acc[j].w, sc.w, sh.w);
-    o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
+    if (out_kind == OP_F32) {   // exact path for the fp32 reference mode
+      o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
+    } else {
+      o.x *= sigmoidf_fast(o.x); o.y *= sigmoidf_fast(o.y); o.z *= sigmoidf_fast(o.z); o.w *= sigmoidf_fast(o.w);
+    }
     store_kind4(y, ((long)b * T + t) * C + c, out_kind, o.x, o.y, o.z, o.w);
   }
 }

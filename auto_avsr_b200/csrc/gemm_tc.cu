@@ -371,7 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           const float* sb = s_vec + c;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) val[j] = (val[j] + sb[j]) * sigmoidf_acc(gate[j] + sb[64 + j]);
+          for (int j = 0; j < 32; ++j) val[j] = (val[j] + sb[j]) * sigmoidf_fast(gate[j] + sb[64 + j]);
           stage_write_f32(stg, lane, val, false);
           __syncwarp();
 #pragma unroll
