@@ -139,13 +139,11 @@ __device__ __forceinline__ void emit_linear_op(const EpiParams& p, int m, int n,
   if (m >= p.M || n >= p.N) return;
   *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(p.out) + (long)m * p.ldo + n) = pay;
 }
+// QKV: row (b, t) and column (head h, offset d0) already decoded by the caller (no per-element divisions)
 template <typename TOp>
-__device__ __forceinline__ void emit_heads(const EpiParams& p, void* base, int m, int n, uint4 pay) {  // QK
-  if (m >= p.M || n >= p.N) return;
-  const int D = p.H * kHeadDim;
-  const int b = m / p.T, t = m - b * p.T;
-  const int nn = n % D;                              // q | k | v segments share the head-major layout
-  const int h = nn >> 6, d0 = nn & 63;
+__device__ __forceinline__ void emit_heads(const EpiParams& p, void* base, bool ok, int b, int t, int h, int d0,
+                                           uint4 pay) {
+  if (!ok) return;
   *reinterpret_cast<uint4*>(reinterpret_cast<TOp*>(base) + (((long)b * p.H + h) * p.T + t) * kHeadDim + d0) = pay;
 }
 template <typename TOp>
@@ -463,6 +461,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float* sb = s_vec + c;
 #pragma unroll
             for (int j = 0; j < OC; ++j) v[j] += sb[j];
+            // decode once per chunk / per lane: column -> (segment, head, offset); rows -> (utterance, frame)
+            const int np = n + pc * ONE;
+            const int seg = np / D, nn = np - seg * D;
+            const int hh = nn >> 6, d0 = nn & 63;
+            int rb[8], rt[8];
+            bool rok[8];
+            {
+              const int mrow = mw + pr;                    // this lane's first row; the others follow 4 rows apart
+              int bb = mrow / ep.T, tt = mrow - bb * ep.T;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                rb[it] = bb; rt[it] = tt; rok[it] = (mrow + it * 4 < ep.M) && (np < ep.N);
+                tt += 4;
+                while (tt >= ep.T) { tt -= ep.T; ++bb; }
+              }
+            }
             if (n < D) {                                     // q: two outputs, q + pos_bias_u and q + pos_bias_v
               const float* su = s_vec + BN + c;
 #pragma unroll
@@ -471,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                emit_heads<TOp>(ep, ep.qu, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+                emit_heads<TOp>(ep, ep.qu, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
               __syncwarp();
               // second output: re-read the accumulator chunk (cheaper than keeping two register copies)
 #pragma unroll
@@ -484,14 +498,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __syncwarp();
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                emit_heads<TOp>(ep, ep.qv, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+                emit_heads<TOp>(ep, ep.qv, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
               __syncwarp();
             } else {
               StageOp<TOp>::write(stg, lane, v);
               __syncwarp();
+              void* dst = n < 2 * D ? ep.kk : ep.vt;
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                emit_heads<TOp>(ep, n < 2 * D ? ep.kk : ep.vt, mw + it * 4 + pr, n + pc * ONE, stage_read(stg, it, lane));
+                emit_heads<TOp>(ep, dst, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
               __syncwarp();
             }
           } else {
