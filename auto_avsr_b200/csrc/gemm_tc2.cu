@@ -109,7 +109,9 @@ __device__ __forceinline__ uint4 t2_stage_read(const uint8_t* stg, int it, int l
   return *reinterpret_cast<const uint4*>(stg + (it * 4 + (lane >> 3)) * T2_STG_ROW + (lane & 7) * 16);
 }
 
-template <int BNP>
+// RELU / RESID are compile-time: a predicated-off instruction still takes an issue slot, and this epilogue is not
+// overlapped with anything (one tile per cluster).
+template <int BNP, bool RELU, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_n,
                 EpiParams ep) {
@@ -210,12 +212,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
         const float* sb = s_bias + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+        for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
         t2_stage_f32(stg, lane, v);
         __syncwarp();
         const int n = n0 + c + pc * 4;
         float4 r[8];
-        if (ep.resid) {
+        if (RESID) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int m = mw + it * 4 + pr;
@@ -228,7 +230,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int m = mw + it * 4 + pr;
           const uint4 pay = t2_stage_read(stg, it, lane);
           float4 o = *reinterpret_cast<const float4*>(&pay);
-          if (ep.resid) {
+          if (RESID) {
             o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
             o.z = r[it].z + ep.alpha * o.z; o.w = r[it].w + ep.alpha * o.w;
           }
@@ -237,15 +239,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
       }
     } else {                                               // fp16 operand destination (FFN hidden)
-#pragma unroll 1
-      for (int c = cb; c < ce; c += 64) {
-        float v[64];
-        tmem_ld32(trow + c, v);
-        tmem_ld32(trow + c + 32, v + 32);
+      // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted, staged and stored
+      constexpr int NC = (BNP / 2) / 64;                   // 64-column chunks per warp (4 for the 256x512 pair tile)
+      float va[64], vb[64];
+      tmem_ld32(trow + cb, va);
+      tmem_ld32(trow + cb + 32, va + 32);
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) {
+        const int c = cb + ci * 64;
+        float* v = (ci & 1) ? vb : va;
+        float* vn = (ci & 1) ? va : vb;
         tmem_ld_wait();
+        if (ci + 1 < NC) {
+          tmem_ld32(trow + c + 64, vn);
+          tmem_ld32(trow + c + 96, vn + 32);
+        }
         const float* sb = s_bias + c;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) { v[j] += sb[j]; if (ep.relu) v[j] = fmaxf(v[j], 0.f); }
+        for (int j = 0; j < 64; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
         t2_stage_f16(stg, lane, v);
         __syncwarp();
 #pragma unroll
@@ -267,16 +278,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+template <int BNP, bool RELU, bool RESID>
+static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, int K, int tiles_n, const EpiParams& ep,
+                        cudaStream_t st) {
+  using Cfg = T2Cfg<BNP>;
+  AVSR_SET_MAX_SMEM((gemm_tc2_kernel<BNP, RELU, RESID>), Cfg::kSmem);
+  AVSR_LAUNCH((gemm_tc2_kernel<BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
+  return AVSR_OK;
+}
+
 template <int BNP>
 static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   CUtensorMap tmA, tmB;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 2));
   AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kBRows, 2));
-  AVSR_SET_MAX_SMEM(gemm_tc2_kernel<BNP>, Cfg::kSmem);
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
-  AVSR_LAUNCH(gemm_tc2_kernel<BNP>, 2 * tiles_m * tiles_n, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
-  return AVSR_OK;
+  const int grid = 2 * tiles_m * tiles_n;
+  const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
+  if (relu && resid) return launch_tc2_k<BNP, true, true>(tmA, tmB, grid, K, tiles_n, ep, st);
+  if (relu) return launch_tc2_k<BNP, true, false>(tmA, tmB, grid, K, tiles_n, ep, st);
+  if (resid) return launch_tc2_k<BNP, false, true>(tmA, tmB, grid, K, tiles_n, ep, st);
+  return launch_tc2_k<BNP, false, false>(tmA, tmB, grid, K, tiles_n, ep, st);
 }
 
 // Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.
