@@ -263,8 +263,9 @@ int gemm_simt(int mode, const float* A, const float* Bw, int M, int N, int K, co
 // tcgen05 GEMM (gemm_tc.cu); opk = OP_TF32 (A, Bw are float) or OP_F16 (A, Bw are __half)
 int gemm_tc(int mode, int opk, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 
-// two-SM (cta_group::2) GEMM for fp16 EPI_LINEAR (gemm_tc2.cu): *handled = 1 when it took the problem
-int gemm_tc2_try(const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int* handled);
+// two-SM (cta_group::2) GEMM for fp16 EPI_LINEAR / EPI_QK / EPI_GLU (gemm_tc2.cu): *handled = 1 when it took the problem
+int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st,
+                 int* handled);
 
 // elementwise.cu
 int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStream_t st);

@@ -13,6 +13,7 @@
 // One pair-tile per cluster (the FFN shapes give 42 pair-tiles <= 74 pairs), so no accumulator double buffering.
 // fp16 operands, EPI_LINEAR only; everything else uses gemm_tc.cu.
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "sm100.cuh"
 
 namespace avsr {
@@ -20,8 +21,7 @@ namespace avsr {
 using namespace sm100;
 
 constexpr int T2_THREADS = 320;
-constexpr int T2_STG_ROW = 144;
-constexpr int T2_STG_WARP = 32 * T2_STG_ROW;
+constexpr int T2_STG_WARP = STG_WARP;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address with the CTA-pair peer bit cleared = leader CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -76,7 +76,7 @@ struct T2Cfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = kNSub * kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;         // per CTA
-  static constexpr int kVecBytes = BNP * 4;
+  static constexpr int kVecBytes = 3 * BNP * 4;   // bias / pos_bias_u / pos_bias_v of the tile's columns
   static constexpr int kFixed = 1024 + 256 + kVecBytes + 8 * T2_STG_WARP;
   static constexpr int kStagesFit = (222 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -85,33 +85,9 @@ struct T2Cfg {
   static_assert(kStages >= 2 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "bad pair tile");
 };
 
-// lane-per-row staging writes / transposed reads (same scheme as gemm_tc.cu)
-__device__ __forceinline__ void t2_stage_f32(uint8_t* stg, int lane, const float* o) {
-  uint8_t* row = stg + lane * T2_STG_ROW;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(row + 16 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-}
-__device__ __forceinline__ void t2_stage_f16(uint8_t* stg, int lane, const float* o) {
-  uint8_t* row = stg + lane * T2_STG_ROW;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 t;
-    __half2 h0 = __halves2half2(to_half_sat(o[8 * j]), to_half_sat(o[8 * j + 1]));
-    __half2 h1 = __halves2half2(to_half_sat(o[8 * j + 2]), to_half_sat(o[8 * j + 3]));
-    __half2 h2 = __halves2half2(to_half_sat(o[8 * j + 4]), to_half_sat(o[8 * j + 5]));
-    __half2 h3 = __halves2half2(to_half_sat(o[8 * j + 6]), to_half_sat(o[8 * j + 7]));
-    t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
-    t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(row + 16 * j) = t;
-  }
-}
-__device__ __forceinline__ uint4 t2_stage_read(const uint8_t* stg, int it, int lane) {
-  return *reinterpret_cast<const uint4*>(stg + (it * 4 + (lane >> 3)) * T2_STG_ROW + (lane & 7) * 16);
-}
-
 // RELU / RESID are compile-time: a predicated-off instruction still takes an issue slot, and this epilogue is not
 // overlapped with anything (one tile per cluster).
-template <int BNP, bool RELU, bool RESID>
+template <int MODE, int BNP, bool RELU, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_n,
                 EpiParams ep) {
@@ -198,13 +174,95 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int c = threadIdx.x - 64; c < BNP; c += T2_THREADS - 64) {
       const int n = n0 + c;
       s_bias[c] = (ep.bias && n < ep.N) ? ep.bias[n] : 0.f;
+      if constexpr (MODE == EPI_QK) {
+        const bool isq = n < ep.H * kHeadDim;
+        s_bias[BNP + c] = isq ? ep.pos_u[n] : 0.f;
+        s_bias[2 * BNP + c] = isq ? ep.pos_v[n] : 0.f;
+      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int mw = m0 + (int)rank * 128 + q * 32;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (!ep.round_out) {                                   // fp32 destination (+ residual)
+    if constexpr (MODE == EPI_GLU) {
+      // interleaved pointwise_cov1: per 128-column group, value columns [g, g+64), their gates 64 further
+#pragma unroll 1
+      for (int g = 0; g < BNP; g += 128) {
+        const int c = g + chalf * 32;
+        float val[32], gate[32];
+        tmem_ld32(trow + c, val);
+        tmem_ld32(trow + c + 64, gate);
+        tmem_ld_wait();
+        const float* sb = s_bias + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] = (val[j] + sb[j]) * sigmoidf_fast(gate[j] + sb[64 + j]);
+        stage_write_f32(stg, lane, val, false);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) emit_glu(ep, mw + it * 4 + pr, n0 + c + pc * 4, stage_read(stg, it, lane));
+        __syncwarp();
+      }
+    } else if constexpr (MODE == EPI_QK) {
+      const int D = ep.H * kHeadDim;
+#pragma unroll 1
+      for (int c = cb; c < ce; c += 64) {
+        float v[64];
+        tmem_ld32(trow + c, v);
+        tmem_ld32(trow + c + 32, v + 32);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        const float* sb = s_bias + c;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] += sb[j];
+        const int np = n + pc * 8;
+        const int seg = np / D, nn = np - seg * D;
+        const int hh = nn >> 6, d0 = nn & 63;
+        int rb[8], rt[8];
+        bool rok[8];
+        {
+          const int mrow = mw + pr;
+          int bb = mrow / ep.T, tt = mrow - bb * ep.T;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            rb[it] = bb; rt[it] = tt; rok[it] = (mrow + it * 4 < ep.M) && (np < ep.N);
+            tt += 4;
+            while (tt >= ep.T) { tt -= ep.T; ++bb; }
+          }
+        }
+        if (n < D) {                                       // q: q + pos_bias_u and q + pos_bias_v
+          const float* su = s_bias + BNP + c;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] += su[j];
+          stage_write_f16(stg, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            emit_heads<__half>(ep, ep.qu, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
+          __syncwarp();
+          tmem_ld32(trow + c, v);
+          tmem_ld32(trow + c + 32, v + 32);
+          tmem_ld_wait();
+          const float* sv = s_bias + 2 * BNP + c;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] += sb[j] + sv[j];
+          stage_write_f16(stg, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            emit_heads<__half>(ep, ep.qv, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
+          __syncwarp();
+        } else {
+          stage_write_f16(stg, lane, v);
+          __syncwarp();
+          void* dst = n < 2 * D ? ep.kk : ep.vt;
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            emit_heads<__half>(ep, dst, rok[it], rb[it], rt[it], hh, d0, stage_read(stg, it, lane));
+          __syncwarp();
+        }
+      }
+    } else if (!ep.round_out) {                            // fp32 destination (+ residual)
 #pragma unroll 1
       for (int c = cb; c < ce; c += 32) {
         float v[32];
@@ -213,7 +271,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const float* sb = s_bias + c;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
-        t2_stage_f32(stg, lane, v);
+        stage_write_f32(stg, lane, v, false);
         __syncwarp();
         const int n = n0 + c + pc * 4;
         float4 r[8];
@@ -228,7 +286,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = mw + it * 4 + pr;
-          const uint4 pay = t2_stage_read(stg, it, lane);
+          const uint4 pay = stage_read(stg, it, lane);
           float4 o = *reinterpret_cast<const float4*>(&pay);
           if (RESID) {
             o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
@@ -257,12 +315,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const float* sb = s_bias + c;
 #pragma unroll
         for (int j = 0; j < 64; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
-        t2_stage_f16(stg, lane, v);
+        stage_write_f16(stg, lane, v);
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = mw + it * 4 + pr, n = n0 + c + pc * 8;
-          const uint4 pay = t2_stage_read(stg, it, lane);
+          const uint4 pay = stage_read(stg, it, lane);
           if (m < ep.M && n < ep.N) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + (long)m * ep.ldo + n) = pay;
         }
         __syncwarp();
@@ -278,16 +336,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BNP, bool RELU, bool RESID>
+template <int MODE, int BNP, bool RELU, bool RESID>
 static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, int K, int tiles_n, const EpiParams& ep,
                         cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
-  AVSR_SET_MAX_SMEM((gemm_tc2_kernel<BNP, RELU, RESID>), Cfg::kSmem);
-  AVSR_LAUNCH((gemm_tc2_kernel<BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
+  AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
+  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
   return AVSR_OK;
 }
 
-template <int BNP>
+template <int MODE, int BNP>
 static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   CUtensorMap tmA, tmB;
@@ -295,35 +353,47 @@ static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, co
   AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kBRows, 2));
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
   const int grid = 2 * tiles_m * tiles_n;
-  const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
-  if (relu && resid) return launch_tc2_k<BNP, true, true>(tmA, tmB, grid, K, tiles_n, ep, st);
-  if (relu) return launch_tc2_k<BNP, true, false>(tmA, tmB, grid, K, tiles_n, ep, st);
-  if (resid) return launch_tc2_k<BNP, false, true>(tmA, tmB, grid, K, tiles_n, ep, st);
-  return launch_tc2_k<BNP, false, false>(tmA, tmB, grid, K, tiles_n, ep, st);
+  if constexpr (MODE == EPI_LINEAR) {
+    const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
+    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, grid, K, tiles_n, ep, st);
+    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, grid, K, tiles_n, ep, st);
+    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, grid, K, tiles_n, ep, st);
+  }
+  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, grid, K, tiles_n, ep, st);
 }
 
 // Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.
-int gemm_tc2_try(const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int* handled) {
+int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st,
+                 int* handled) {
   *handled = 0;
   static const bool enabled = [] { const char* e = getenv("AVSR_B200_2CTA"); return !(e && e[0] == '0'); }();
   if (!enabled || K % 64 != 0 || N % 8 != 0 || M < 256) return AVSR_OK;
-  if ((ep.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(ep.out) & 15) || (reinterpret_cast<uintptr_t>(ep.resid) & 15))
+  if (mode != EPI_LINEAR && mode != EPI_QK && mode != EPI_GLU) return AVSR_OK;
+  if (mode == EPI_LINEAR &&
+      ((ep.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(ep.out) & 15) || (reinterpret_cast<uintptr_t>(ep.resid) & 15)))
     return AVSR_OK;
+  if (mode == EPI_GLU && ((ep.ldo % 4) != 0 || N % 128 != 0)) return AVSR_OK;
+  if (mode == EPI_QK && (N % 128 != 0 || (ep.H * kHeadDim) % 64 != 0)) return AVSR_OK;
   // Pair-tile width: per-SM ingest ~ (128 + BNP/2) * K * 2 bytes shrinks with BNP, so take the NARROWEST width whose
   // pair-tiles still fit one wave of 74 clusters (a second wave would double the time of this one-tile-per-cluster
-  // kernel): FFN w_1 (N = 3072) -> 512 (42 pairs), FFN w_2 / out / pw2 (N = 768) -> 128 (42 pairs).
+  // kernel): FFN w_1 (N = 3072) -> 512 (42 pairs), FFN w_2 / out / pw2 (N = 768) -> 128 (42 pairs), QKV (N = 2304)
+  // -> 256 (63 pairs), pw1+GLU (N = 1536) -> 256 (42 pairs; GLU needs whole 128-column groups).
   const int tiles_m = cdiv(M, 256);
   int bnp = 0;
   for (int cand : {128, 256, 512}) {
+    if (mode == EPI_GLU && cand < 128) continue;
+    if (mode != EPI_LINEAR && cand == 512) continue;           // QK / GLU instantiated for 128 and 256 only
     if (N % cand == 0 && tiles_m * (N / cand) <= 74) { bnp = cand; break; }
   }
   if (!bnp) return AVSR_OK;
   *handled = 1;
   const __half* a = reinterpret_cast<const __half*>(A);
   const __half* b = reinterpret_cast<const __half*>(Bw);
-  if (bnp == 512) return launch_tc2<512>(a, b, M, N, K, ep, st);
-  if (bnp == 256) return launch_tc2<256>(a, b, M, N, K, ep, st);
-  return launch_tc2<128>(a, b, M, N, K, ep, st);
+  if (mode == EPI_QK) return bnp == 256 ? launch_tc2<EPI_QK, 256>(a, b, M, N, K, ep, st) : launch_tc2<EPI_QK, 128>(a, b, M, N, K, ep, st);
+  if (mode == EPI_GLU) return bnp == 256 ? launch_tc2<EPI_GLU, 256>(a, b, M, N, K, ep, st) : launch_tc2<EPI_GLU, 128>(a, b, M, N, K, ep, st);
+  if (bnp == 512) return launch_tc2<EPI_LINEAR, 512>(a, b, M, N, K, ep, st);
+  if (bnp == 256) return launch_tc2<EPI_LINEAR, 256>(a, b, M, N, K, ep, st);
+  return launch_tc2<EPI_LINEAR, 128>(a, b, M, N, K, ep, st);
 }
 
 }  // namespace avsr
