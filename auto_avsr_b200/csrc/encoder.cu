@@ -203,8 +203,17 @@ static int run_gemm(int prec, int mode, const void* A, const void* Bw, int M, in
 }
 
 // the part of the forward that only touches workspace buffers (what a plan captures into its graph)
+// `aux` (optional): a second stream + two events.  The rel-pos table and the stacked linear_pos GEMM only feed the
+// attention kernels, so they are forked onto `aux.stream` and joined right before layer 0's attention; inside a
+// captured graph this becomes a parallel branch that overlaps layer 0's macaron FFN (the work is still done every
+// forward -- nothing is cached across steps).
+struct AuxFork {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
 static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int B, int T,
-                        const int32_t* lengths, float* taps, int prec, cudaStream_t st) {
+                        const int32_t* lengths, float* taps, int prec, cudaStream_t st, const AuxFork* aux = nullptr) {
   const int N = B * T, D = c.d_model, F = c.linear_units, H = c.n_heads, L = c.num_blocks;
   const int opk = operand_kind(prec);           // storage of every tensor that feeds a contraction
   const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
@@ -213,12 +222,19 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
   // split-K tile counters must be zero on entry (they re-arm themselves; this covers a first use / an aborted run)
   AVSR_CUDA_TRY(cudaMemsetAsync(W.counters, 0, kSplitCounters * sizeof(int), st));
   // pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
-  AVSR_TRY(launch_sinusoid(W.pe, T, D, opk, st));
+  cudaStream_t ps = st;
+  if (aux) {
+    AVSR_CUDA_TRY(cudaEventRecord(aux->fork, st));
+    AVSR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    ps = aux->stream;
+  }
+  AVSR_TRY(launch_sinusoid(W.pe, T, D, opk, ps));
   {
     EpiParams e{};
     e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = opr;
-    AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, st));
+    AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, ps));
   }
+  if (aux) AVSR_CUDA_TRY(cudaEventRecord(aux->join, ps));
   // v^T pad columns [T, Tp) must be finite (FP32 / TF32 paths; the F16 path keeps V un-transposed)
   if (W.Tp != T && prec != AVSR_PREC_F16)
     AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
@@ -254,6 +270,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
         AVSR_TRY(run_gemm(prec, EPI_VT, op_offset(w.qk_w, (size_t)2 * D * D, prec), W.xn, D, N, D, v, st));
       }
     }
+    if (l == 0 && aux) AVSR_CUDA_TRY(cudaStreamWaitEvent(st, aux->join, 0));   // the pos tables are ready
     {
       const void* pos_l = op_offset(W.pos, (size_t)l * H * W.Rp * kHeadDim, prec);
       if (prec == AVSR_PREC_F16)
@@ -425,18 +442,30 @@ int avsr_plan_create(const AvsrEncoderConfig* cfg, const void* prepared, int B, 
   // warm-up outside capture: sets function attributes (dynamic smem opt-in) that capture must not do lazily
   fill_lengths_kernel<<<cdiv(B, 128), 128, 0, st>>>(W.lengths, nullptr, B, T);
   g_launches.fetch_add(1);
-  int rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st);
-  if (rc == AVSR_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+  AuxFork aux;
+  if (cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("plan: cannot create the auxiliary stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return AVSR_E_CUDA;
+  }
+  auto drop_aux = [&]() {
+    cudaEventDestroy(aux.fork); cudaEventDestroy(aux.join); cudaStreamDestroy(aux.stream);
+  };
+  int rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st, &aux);
+  if (rc == AVSR_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaStreamSynchronize(aux.stream) != cudaSuccess)) {
     set_error("plan warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
     rc = AVSR_E_CUDA;
   }
-  if (rc != AVSR_OK) { delete p; return rc; }
+  if (rc != AVSR_OK) { drop_aux(); delete p; return rc; }
   cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
-  if (e != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); delete p; return AVSR_E_CUDA; }
+  if (e != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); drop_aux(); delete p; return AVSR_E_CUDA; }
   const uint64_t before = g_launches.load();
-  rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st);
+  rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st, &aux);   // aux joins the capture
   g_launches.store(before);  // captured launches are counted when the graph is replayed
   e = cudaStreamEndCapture(st, &p->graph);
+  drop_aux();
   if (rc != AVSR_OK) { if (p->graph) cudaGraphDestroy(p->graph); delete p; return rc; }
   if (e != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); delete p; return AVSR_E_CUDA; }
   e = cudaGraphInstantiate(&p->exec, p->graph, 0);
