@@ -68,29 +68,35 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
                : "memory");
 }
 
+// A pair tile of width BNP is covered by up to two MMA sub-blocks (UMMA N <= 256): 128 -> {128}, 256 -> {256},
+// 384 -> {256, 128}, 512 -> {256, 256}.  Each CTA stages half of every sub-block's B rows.
 template <int BNP>
 struct T2Cfg {
-  static constexpr int kNSub = BNP > 256 ? BNP / 256 : 1;       // MMAs per k-step (UMMA N <= 256)
-  static constexpr int kUmmaN = BNP / kNSub;                    // 128 or 256
-  static constexpr int kBRows = kUmmaN / 2;                     // B rows per CTA per sub-block
+  static constexpr int kNSub = BNP > 256 ? 2 : 1;
+  static constexpr int kN0 = BNP > 256 ? 256 : BNP;              // width of sub-block 0
+  static constexpr int kN1 = BNP > 256 ? BNP - 256 : 0;          // width of sub-block 1 (0, 128 or 256)
+  static constexpr int kBRowsTotal = BNP / 2;                    // B rows per CTA per stage
   static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = kNSub * kBRows * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;         // per CTA
+  static constexpr int kBBytes = kBRowsTotal * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;          // per CTA
   static constexpr int kVecBytes = 3 * BNP * 4;   // bias / pos_bias_u / pos_bias_v of the tile's columns
   static constexpr int kFixed = 1024 + 256 + kVecBytes + 8 * T2_STG_WARP;
   static constexpr int kStagesFit = (222 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
-  static constexpr int kTmemCols = BNP < 32 ? 32 : BNP;
-  static_assert(kStages >= 2 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "bad pair tile");
+  static constexpr int kTmemCols = BNP <= 128 ? 128 : (BNP <= 256 ? 256 : 512);
+  static_assert(kStages >= 2 && BNP % 128 == 0 && BNP <= 512, "bad pair tile");
+  __host__ __device__ static constexpr int sub_n(int j) { return j == 0 ? kN0 : kN1; }
+  __host__ __device__ static constexpr int sub_col(int j) { return j == 0 ? 0 : kN0; }          // first tile column
+  __host__ __device__ static constexpr int sub_brow(int j) { return j == 0 ? 0 : kN0 / 2; }     // first B smem row
 };
 
 // RELU / RESID are compile-time: a predicated-off instruction still takes an issue slot, and this epilogue is not
 // overlapped with anything (one tile per cluster).
 template <int MODE, int BNP, bool RELU, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int tiles_n,
-                EpiParams ep) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmB1, int K, int tiles_n, EpiParams ep) {
   using Cfg = T2Cfg<BNP>;
   constexpr int S = Cfg::kStages;
   constexpr int KE = 64;   // halves per 128-byte k-block
@@ -116,6 +122,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (Cfg::kNSub == 2) tma_prefetch_desc(&tmB1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -137,15 +144,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes); // bytes of BOTH CTAs land on the leader's barrier
         const uint32_t dst = base + s * Cfg::kStageBytes;
         tma_load_2d_2sm(dst, &tmA, kb * KE, m0 + (int)rank * 128, full_bar(s));
-#pragma unroll
-        for (int j = 0; j < Cfg::kNSub; ++j)
-          tma_load_2d_2sm(dst + Cfg::kABytes + j * (Cfg::kBRows * 128), &tmB, kb * KE,
-                          n0 + j * Cfg::kUmmaN + (int)rank * Cfg::kBRows, full_bar(s));
+        // sub-block 0 with box tmB (kN0/2 rows), sub-block 1 with box tmB1 (kN1/2 rows)
+        tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kb * KE, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(s));
+        if constexpr (Cfg::kNSub == 2)
+          tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kb * KE,
+                          n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(s));
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(256, Cfg::kUmmaN);
+      const uint32_t idesc0 = umma_idesc_f16(256, Cfg::kN0);
+      const uint32_t idesc1 = umma_idesc_f16(256, Cfg::kNSub == 2 ? Cfg::kN1 : Cfg::kN0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
@@ -155,10 +164,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t a_desc = umma_desc_sw128(a_addr);
 #pragma unroll
         for (int j = 0; j < Cfg::kNSub; ++j) {
-          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + j * (Cfg::kBRows * 128));
+          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + Cfg::sub_brow(j) * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_f16_2sm(tmem_base + j * Cfg::kUmmaN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            mma_f16_2sm(tmem_base + Cfg::sub_col(j), a_desc + 2 * k, b_desc + 2 * k, j == 0 ? idesc0 : idesc1, (kb | k) != 0);
         }
         tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
       }
@@ -337,29 +346,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int MODE, int BNP, bool RELU, bool RESID>
-static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, int K, int tiles_n, const EpiParams& ep,
-                        cudaStream_t st) {
+static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, int grid, int K,
+                        int tiles_n, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
-  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, K, tiles_n, ep);
+  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n, ep);
   return AVSR_OK;
 }
 
 template <int MODE, int BNP>
 static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmB1;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 2));
-  AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kBRows, 2));
+  AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kN0 / 2, 2));
+  AVSR_TRY(make_tmap_2d(&tmB1, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kNSub == 2 ? Cfg::kN1 / 2 : Cfg::kN0 / 2, 2));
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
   const int grid = 2 * tiles_m * tiles_n;
   if constexpr (MODE == EPI_LINEAR) {
     const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
-    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, grid, K, tiles_n, ep, st);
-    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, grid, K, tiles_n, ep, st);
-    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, grid, K, tiles_n, ep, st);
+    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
+    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
+    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
   }
-  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, grid, K, tiles_n, ep, st);
+  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
 }
 
 // Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.
@@ -376,13 +386,13 @@ int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, c
   if (mode == EPI_QK && (N % 128 != 0 || (ep.H * kHeadDim) % 64 != 0)) return AVSR_OK;
   // Pair-tile width: per-SM ingest ~ (128 + BNP/2) * K * 2 bytes shrinks with BNP, so take the NARROWEST width whose
   // pair-tiles still fit one wave of 74 clusters (a second wave would double the time of this one-tile-per-cluster
-  // kernel): FFN w_1 (N = 3072) -> 512 (42 pairs), FFN w_2 / out / pw2 (N = 768) -> 128 (42 pairs), QKV (N = 2304)
+  // kernel): FFN w_1 (N = 3072) -> 384 (56 pairs), FFN w_2 / out / pw2 (N = 768) -> 128 (42 pairs), QKV (N = 2304)
   // -> 256 (63 pairs), pw1+GLU (N = 1536) -> 256 (42 pairs; GLU needs whole 128-column groups).
   const int tiles_m = cdiv(M, 256);
   int bnp = 0;
-  for (int cand : {128, 256, 512}) {
+  for (int cand : {128, 256, 384, 512}) {
     if (mode == EPI_GLU && cand < 128) continue;
-    if (mode != EPI_LINEAR && cand == 512) continue;           // QK / GLU instantiated for 128 and 256 only
+    if (mode != EPI_LINEAR && cand > 256) continue;            // QK / GLU instantiated for 128 and 256 only
     if (N % cand == 0 && tiles_m * (N / cand) <= 74) { bnp = cand; break; }
   }
   if (!bnp) return AVSR_OK;
@@ -392,6 +402,7 @@ int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, c
   if (mode == EPI_QK) return bnp == 256 ? launch_tc2<EPI_QK, 256>(a, b, M, N, K, ep, st) : launch_tc2<EPI_QK, 128>(a, b, M, N, K, ep, st);
   if (mode == EPI_GLU) return bnp == 256 ? launch_tc2<EPI_GLU, 256>(a, b, M, N, K, ep, st) : launch_tc2<EPI_GLU, 128>(a, b, M, N, K, ep, st);
   if (bnp == 512) return launch_tc2<EPI_LINEAR, 512>(a, b, M, N, K, ep, st);
+  if (bnp == 384) return launch_tc2<EPI_LINEAR, 384>(a, b, M, N, K, ep, st);
   if (bnp == 256) return launch_tc2<EPI_LINEAR, 256>(a, b, M, N, K, ep, st);
   return launch_tc2<EPI_LINEAR, 128>(a, b, M, N, K, ep, st);
 }
