@@ -85,7 +85,7 @@ struct T2Cfg {
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = BNP <= 128 ? 128 : (BNP <= 256 ? 256 : 512);
-  static_assert(kStages >= 2 && BNP % 128 == 0 && BNP <= 512, "bad pair tile");
+  static_assert(kStages >= 2 && BNP % 32 == 0 && BNP <= 512, "bad pair tile");
   __host__ __device__ static constexpr int sub_n(int j) { return j == 0 ? kN0 : kN1; }
   __host__ __device__ static constexpr int sub_col(int j) { return j == 0 ? 0 : kN0; }          // first tile column
   __host__ __device__ static constexpr int sub_brow(int j) { return j == 0 ? 0 : kN0 / 2; }     // first B smem row
@@ -178,7 +178,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
     uint8_t* stg = stg_base + (warp - 2) * T2_STG_WARP;
-    const int cb = chalf * (BNP / 2), ce = cb + BNP / 2;
+    // column ranges of the two warps that share a lane quarter (whole 32-column chunks; 96 = 64 + 32)
+    const int cb = (BNP == 96) ? chalf * 64 : chalf * (BNP / 2);
+    const int ce = (BNP == 96) ? (chalf ? 96 : 64) : cb + BNP / 2;
     const int pr = lane >> 3, pc = lane & 7;
     for (int c = threadIdx.x - 64; c < BNP; c += T2_THREADS - 64) {
       const int n = n0 + c;
@@ -390,6 +392,7 @@ int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, c
   // -> 256 (63 pairs), pw1+GLU (N = 1536) -> 256 (42 pairs; GLU needs whole 128-column groups).
   const int tiles_m = cdiv(M, 256);
   int bnp = 0;
+  // (a 256 x 96 tile -- 56 clusters for N = 768 -- was measured slower than 256 x 128: 1.862 vs 1.838 ms per forward)
   for (int cand : {128, 256, 384, 512}) {
     if (mode == EPI_GLU && cand < 128) continue;
     if (mode != EPI_LINEAR && cand > 256) continue;            // QK / GLU instantiated for 128 and 256 only
