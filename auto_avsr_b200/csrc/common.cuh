@@ -267,13 +267,31 @@ int gemm_tc(int mode, int opk, const void* A, const void* Bw, int M, int N, int 
 int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st,
                  int* handled);
 
+// deferred split-K (gemm_tc2.cu): plan returns 1 and fills bnp / nsplit when the shape qualifies; the GEMM writes
+// partial[s][M][N] (raw fp32 k-slice sums) and the consuming LayerNorm finishes the residual update (LnParts)
+int gemm_tc2_splitk_plan(int M, int N, int K, int* bnp, int* nsplit);
+int gemm_tc2_splitk(const void* A, const void* Bw, int M, int N, int K, float* partial, int bnp, int nsplit,
+                    cudaStream_t st);
+
+// Residual update folded into a LayerNorm's load: row = x + alpha * (bias + part[0] + part[1] + ... ) (fixed order,
+// so the result does not depend on scheduling); the updated row is written to x_out when that is not already the
+// LayerNorm's own fp32 output.
+struct LnParts {
+  const float* part = nullptr;   // [nparts][rows][d]
+  int nparts = 0;
+  long stride = 0;               // rows * d
+  const float* bias = nullptr;   // [d]
+  float alpha = 0.f;
+  float* x_out = nullptr;        // optional [rows][d]
+};
+
 // elementwise.cu
 int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStream_t st);
 // `out_kind` is an OperandKind: how y / pe is stored
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
-                     cudaStream_t st);
+                     cudaStream_t st, const LnParts* parts = nullptr);
 int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
-                      void* y2, int rows, int d, int out_kind, cudaStream_t st);
+                      void* y2, int rows, int d, int out_kind, cudaStream_t st, const LnParts* parts = nullptr);
 int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st);
 int launch_dwconv_bn_silu(const float* x, const float* wt /*(K,C)*/, const float* scale, const float* shift, void* y,
                           int B, int T, int C, int K, int out_kind, cudaStream_t st);

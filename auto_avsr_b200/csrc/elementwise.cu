@@ -33,9 +33,35 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 // Two-pass mean / centred variance, warp-shuffle reductions.
 constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
 
+// Deferred split-K residual update applied to the row held in v (see LnParts); NP = number of k-slices, a
+// compile-time constant so that every load of the row is issued before the first use.  The caller stores the updated
+// row (pp.x_out) only after ALL its loads: a store in between would serialise them (possible aliasing).
+template <int NP>
+__device__ __forceinline__ void ln_apply_parts(float4 (&v)[8], int lane, int nvec, long row_vec, const LnParts& pp) {
+  if constexpr (NP > 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(pp.bias);
+    const float4* p4 = reinterpret_cast<const float4*>(pp.part) + row_vec;
+    const long sv = pp.stride >> 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nvec) {
+        float4 a = b4[c];
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+          const float4 t = p4[s * sv + c];
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        v[i].x += pp.alpha * a.x; v[i].y += pp.alpha * a.y; v[i].z += pp.alpha * a.z; v[i].w += pp.alpha * a.w;
+      }
+    }
+  }
+}
+
+template <int NP>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may alias y */, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* y,
-                                                        int rows, int d, int out_kind) {
+                                                        int rows, int d, int out_kind, LnParts pp) {
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,10 +83,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int c = i * 32 + lane;
-    if (c < nvec) {
-      v[i] = xr[c];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+    if (c < nvec) v[i] = xr[c];
+  }
+  ln_apply_parts<NP>(v, lane, nvec, (long)warp * nvec, pp);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) / (float)d;
   float q = 0.f;
@@ -78,6 +107,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
     const int c = i * 32 + lane;
     if (c < nvec) {
       const float4 g = gg[i], b = bb[i];
+      if (NP > 0 && pp.x_out) reinterpret_cast<float4*>(pp.x_out)[(long)warp * nvec + c] = v[i];
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x;
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -91,10 +121,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
 // Two chained LayerNorms in one pass over the row: y1 = LN(x; g1, b1) (fp32, may alias x) and
 // y2 = LN(y1; g2, b2) in operand storage -- layer l's norm_final followed by layer l+1's norm_ff_macaron
 // (conformer_encoder.py:161-162 then :113): one read of x instead of two, one launch instead of two.
+template <int NP>
 __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may alias y1 */, const float* __restrict__ g1,
                                                          const float* __restrict__ b1, const float* __restrict__ g2,
                                                          const float* __restrict__ b2, float* y1,
-                                                         void* __restrict__ y2, int rows, int d, int out_kind) {
+                                                         void* __restrict__ y2, int rows, int d, int out_kind,
+                                                         LnParts pp) {
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,7 +147,13 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may a
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int c = i * 32 + lane;
-    if (c < nvec) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    if (c < nvec) v[i] = xr[c];
+  }
+  ln_apply_parts<NP>(v, lane, nvec, (long)warp * nvec, pp);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   float mean = warp_sum(s) / (float)d;
   float q = 0.f;
@@ -167,23 +205,38 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may a
 }
 
 int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
-                      void* y2, int rows, int d, int out_kind, cudaStream_t st) {
+                      void* y2, int rows, int d, int out_kind, cudaStream_t st, const LnParts* parts) {
   AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm2: d=%d must be a multiple of 4 and <= %d", d,
                kLnMaxVec * 128);
   if (rows <= 0) return AVSR_OK;
   const int warps_per_block = 8;
-  AVSR_LAUNCH(layernorm2_kernel, cdiv(rows, warps_per_block), warps_per_block * 32, 0, st, x, g1, b1, g2, b2, y1, y2,
-              rows, d, out_kind);
+  const LnParts pp = parts ? *parts : LnParts{};
+  const int grid = cdiv(rows, warps_per_block), block = warps_per_block * 32;
+  switch (pp.nparts) {
+    case 0: AVSR_LAUNCH(layernorm2_kernel<0>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
+    case 2: AVSR_LAUNCH(layernorm2_kernel<2>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
+    case 3: AVSR_LAUNCH(layernorm2_kernel<3>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
+    case 4: AVSR_LAUNCH(layernorm2_kernel<4>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
+    default: AVSR_REQUIRE(false, "layernorm2: %d k-slices not instantiated (0, 2, 3, 4)", pp.nparts);
+  }
   return AVSR_OK;
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
-                     cudaStream_t st) {
+                     cudaStream_t st, const LnParts* parts) {
   AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                kLnMaxVec * 128);
   if (rows <= 0) return AVSR_OK;
   const int warps_per_block = 8;
-  AVSR_LAUNCH(layernorm_kernel, cdiv(rows, warps_per_block), warps_per_block * 32, 0, st, x, g, b, y, rows, d, out_kind);
+  const LnParts pp = parts ? *parts : LnParts{};
+  const int grid = cdiv(rows, warps_per_block), block = warps_per_block * 32;
+  switch (pp.nparts) {
+    case 0: AVSR_LAUNCH(layernorm_kernel<0>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
+    case 2: AVSR_LAUNCH(layernorm_kernel<2>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
+    case 3: AVSR_LAUNCH(layernorm_kernel<3>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
+    case 4: AVSR_LAUNCH(layernorm_kernel<4>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
+    default: AVSR_REQUIRE(false, "layernorm: %d k-slices not instantiated (0, 2, 3, 4)", pp.nparts);
+  }
   return AVSR_OK;
 }
 

@@ -239,6 +239,16 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
   if (W.Tp != T && prec != AVSR_PREC_F16)
     AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
 
+  // FFN w_2 (K = linear_units) as a deferred split-K GEMM: k-slices land in W.splitk and the LayerNorm that follows
+  // applies x += 0.5 * (sum of slices + b) while it loads the row.  Not with `taps` (they read x between the two).
+  int w2_bnp = 0, w2_split = 0;
+  const bool w2_defer = prec == AVSR_PREC_F16 && !taps && gemm_tc2_splitk_plan(N, D, F, &w2_bnp, &w2_split);
+  auto w2_parts = [&](const float* bias, float* x_out) {
+    LnParts pp;
+    pp.part = W.splitk; pp.nparts = w2_split; pp.stride = (long)N * D; pp.bias = bias; pp.alpha = 0.5f; pp.x_out = x_out;
+    return pp;
+  };
+
   for (int l = 0; l < L; ++l) {
     const LayerPrep& w = P.layers[l];
     auto tap = [&](int s) -> int {
@@ -250,10 +260,17 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     // (for l > 0 the norm_ff_macaron output was produced together with the previous layer's norm_final)
     if (l == 0) AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, opr), st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_resid(N, D, w.ffm_b2, W.x, 0.5f, W.splitk, W.counters), st));
-    AVSR_TRY(tap(0));
+    if (w2_defer) {
+      AVSR_TRY(gemm_tc2_splitk(W.hid, w.ffm_w2, N, D, F, W.splitk, w2_bnp, w2_split, st));
+    } else {
+      AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ffm_w2, N, D, F, epi_resid(N, D, w.ffm_b2, W.x, 0.5f, W.splitk, W.counters), st));
+      AVSR_TRY(tap(0));
+    }
     // (2) rel-pos MHA: x += out(attn(LN(x)))                                  conformer_encoder.py:119-142
-    AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st));
+    {
+      const LnParts pp = w2_parts(w.ffm_b2, W.x);
+      AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st, w2_defer ? &pp : nullptr));
+    }
     {
       EpiParams e{};
       e.M = N; e.bias = w.qk_b; e.T = T; e.H = H; e.pos_u = w.pos_u; e.pos_v = w.pos_v;
@@ -296,15 +313,23 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     // (4) FFN: x += 0.5 * w2(relu(w1 LN(x)))                                  conformer_encoder.py:154-159
     AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, opk, st));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, opr), st));
-    AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_resid(N, D, w.ff_b2, W.x, 0.5f, W.splitk, W.counters), st));
-    AVSR_TRY(tap(3));
+    if (w2_defer) {
+      AVSR_TRY(gemm_tc2_splitk(W.hid, w.ff_w2, N, D, F, W.splitk, w2_bnp, w2_split, st));
+    } else {
+      AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.hid, w.ff_w2, N, D, F, epi_resid(N, D, w.ff_b2, W.x, 0.5f, W.splitk, W.counters), st));
+      AVSR_TRY(tap(3));
+    }
     // (5) x = LN_final(x)                                                     conformer_encoder.py:161-162
     //     fused with the next layer's norm_ff_macaron: one pass writes x (fp32) and xn (operand)
-    if (l + 1 < L) {
-      const LayerPrep& nx = P.layers[l + 1];
-      AVSR_TRY(launch_layernorm2(W.x, w.ln_fin_w, w.ln_fin_b, nx.ln_ffm_w, nx.ln_ffm_b, W.x, W.xn, N, D, opk, st));
-    } else {
-      AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st));
+    {
+      const LnParts pp = w2_parts(w.ff_b2, nullptr);   // the LayerNorm's own fp32 output replaces x
+      const LnParts* ppp = w2_defer ? &pp : nullptr;
+      if (l + 1 < L) {
+        const LayerPrep& nx = P.layers[l + 1];
+        AVSR_TRY(launch_layernorm2(W.x, w.ln_fin_w, w.ln_fin_b, nx.ln_ffm_w, nx.ln_ffm_b, W.x, W.xn, N, D, opk, st, ppp));
+      } else {
+        AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st, ppp));
+      }
     }
     AVSR_TRY(tap(4));
   }

@@ -96,7 +96,7 @@ struct T2Cfg {
 template <int MODE, int BNP, bool RELU, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmB1, int K, int tiles_n, EpiParams ep) {
+                const __grid_constant__ CUtensorMap tmB1, int K, int tiles_n, int nsplit, EpiParams ep) {
   using Cfg = T2Cfg<BNP>;
   constexpr int S = Cfg::kStages;
   constexpr int KE = 64;   // halves per 128-byte k-block
@@ -114,9 +114,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
-  const int pair = blockIdx.x >> 1;
+  // nsplit > 1 (deferred split-K): cluster = (pair-tile, k-slice); the slice's raw fp32 accumulators go to
+  // out + slice * M * ldo and the consumer (the following LayerNorm) sums the slices in a fixed order
+  const int cl = blockIdx.x >> 1;
+  const int pair = cl / nsplit, split = cl - pair * nsplit;
   const int m0 = (pair / tiles_n) * 256, n0 = (pair % tiles_n) * BNP;
-  const int nkb = K / KE;
+  const int nkb = K / KE / nsplit;
+  const int kb0 = split * nkb;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -143,11 +147,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(empty_bar(s), ph ^ 1);                                  // own stage free (leader's commit, multicast)
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes); // bytes of BOTH CTAs land on the leader's barrier
         const uint32_t dst = base + s * Cfg::kStageBytes;
-        tma_load_2d_2sm(dst, &tmA, kb * KE, m0 + (int)rank * 128, full_bar(s));
+        const int kc = (kb0 + kb) * KE;
+        tma_load_2d_2sm(dst, &tmA, kc, m0 + (int)rank * 128, full_bar(s));
         // sub-block 0 with box tmB (kN0/2 rows), sub-block 1 with box tmB1 (kN1/2 rows)
-        tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kb * KE, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(s));
+        tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kc, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(s));
         if constexpr (Cfg::kNSub == 2)
-          tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kb * KE,
+          tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
                           n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(s));
       }
     }
@@ -274,6 +279,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     } else if (!ep.round_out) {                            // fp32 destination (+ residual)
+      float* outp = reinterpret_cast<float*>(ep.out) + (long)split * ep.M * ep.ldo;
 #pragma unroll 1
       for (int c = cb; c < ce; c += 32) {
         float v[32];
@@ -303,7 +309,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
             o.z = r[it].z + ep.alpha * o.z; o.w = r[it].w + ep.alpha * o.w;
           }
-          if (m < ep.M && n < ep.N) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long)m * ep.ldo + n) = o;
+          if (m < ep.M && n < ep.N) *reinterpret_cast<float4*>(outp + (long)m * ep.ldo + n) = o;
         }
         __syncwarp();
       }
@@ -349,29 +355,63 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 template <int MODE, int BNP, bool RELU, bool RESID>
 static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, int grid, int K,
-                        int tiles_n, const EpiParams& ep, cudaStream_t st) {
+                        int tiles_n, int nsplit, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
-  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n, ep);
+  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n,
+              nsplit, ep);
   return AVSR_OK;
 }
 
 template <int MODE, int BNP>
-static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, const EpiParams& ep, cudaStream_t st,
+                      int nsplit = 1) {
   using Cfg = T2Cfg<BNP>;
   CUtensorMap tmA, tmB, tmB1;
   AVSR_TRY(make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 2));
   AVSR_TRY(make_tmap_2d(&tmB, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kN0 / 2, 2));
   AVSR_TRY(make_tmap_2d(&tmB1, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kNSub == 2 ? Cfg::kN1 / 2 : Cfg::kN0 / 2, 2));
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
-  const int grid = 2 * tiles_m * tiles_n;
+  const int grid = 2 * tiles_m * tiles_n * nsplit;
   if constexpr (MODE == EPI_LINEAR) {
     const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
-    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
-    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
-    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
+    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
+    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
+    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
   }
-  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, tmB1, grid, K, tiles_n, ep, st);
+  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
+}
+
+// Deferred split-K plan for a residual GEMM whose consumer is a LayerNorm (the FFN w_2 projections, K = 3072):
+// with one 256 x 128 pair-tile per cluster only 84 SMs work and each ingests K * 384 * 2 bytes; slicing K over
+// `nsplit` clusters per (wider) pair-tile puts <= 74 clusters in one wave with 1/nsplit of the k-blocks each.
+// Returns 0 (no plan) or fills bnp / nsplit.  AVSR_B200_W2SPLIT = "0" | "<bnp>:<nsplit>" overrides.
+int gemm_tc2_splitk_plan(int M, int N, int K, int* bnp, int* nsplit) {
+  static const bool enabled = [] { const char* e = getenv("AVSR_B200_2CTA"); return !(e && e[0] == '0'); }();
+  if (!enabled || M < 256 || N % 8 != 0 || K % 64 != 0) return 0;
+  int wb = 256, ws = 3;
+  if (const char* e = getenv("AVSR_B200_W2SPLIT")) {
+    if (sscanf(e, "%d:%d", &wb, &ws) != 2) return 0;
+  }
+  if ((wb != 256 && wb != 384) || ws < 2 || ws > 4) return 0;   // LayerNorm consumers instantiated for 2, 3, 4 slices
+  const int tiles = cdiv(M, 256) * (N / wb);
+  if (N % wb != 0 || (K / 64) % ws != 0 || K / 64 / ws < 4 || tiles * ws > 74) return 0;
+  *bnp = wb; *nsplit = ws;
+  return 1;
+}
+
+// partial[s][M][N] (fp32, s < nsplit) = A[:, slice s of K] * Bw[:, slice s of K]^T -- no bias, no residual
+int gemm_tc2_splitk(const void* A, const void* Bw, int M, int N, int K, float* partial, int bnp, int nsplit,
+                    cudaStream_t st) {
+  EpiParams ep{};
+  ep.M = M; ep.N = N; ep.out = partial; ep.ldo = N;
+  AVSR_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 15) == 0, "split-K partial buffer must be 16-byte aligned");
+  const __half* a = reinterpret_cast<const __half*>(A);
+  const __half* b = reinterpret_cast<const __half*>(Bw);
+  if (bnp == 384) return launch_tc2<EPI_LINEAR, 384>(a, b, M, N, K, ep, st, nsplit);
+  if (bnp == 256) return launch_tc2<EPI_LINEAR, 256>(a, b, M, N, K, ep, st, nsplit);
+  AVSR_REQUIRE(false, "split-K pair tile %d not instantiated", bnp);
+  return AVSR_OK;
 }
 
 // Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.
