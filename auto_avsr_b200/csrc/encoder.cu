@@ -145,6 +145,7 @@ static inline const void* op_offset(const void* base, size_t elems, int precisio
 }
 
 // ------------------------------------------------------------------ workspace
+constexpr int kMaxBranches = 4;   // a plan may run up to this many batch slices as concurrent graph branches
 struct Workspace {
   float *x, *xn, *hid, *qu, *qv, *kk, *vt, *ctx, *glu, *dw, *pe, *pos;
   float* splitk;      // [kMaxSplits][N][d_model] fp32 partial tiles of the split-K residual GEMMs
@@ -167,10 +168,25 @@ static Workspace layout_workspace(const AvsrEncoderConfig& c, int B, int T, void
   W.pe = cv.take((size_t)W.Rp * D);
   W.pos = cv.take((size_t)c.num_blocks * W.Rp * D);
   W.splitk = cv.take((size_t)kMaxSplits * N * D);
-  W.counters = reinterpret_cast<int*>(cv.take((size_t)kSplitCounters));
+  W.counters = reinterpret_cast<int*>(cv.take((size_t)kSplitCounters * kMaxBranches));
   W.lengths = reinterpret_cast<int32_t*>(cv.take((size_t)B));
   W.bytes = cv.off;
   return W;
+}
+
+// The view of batch elements [b0, b0 + ...) of a workspace laid out for the whole batch: every per-frame buffer is
+// row-major in (b, t), so a slice is a pointer offset (offsets are taken in floats also where a buffer holds halfs:
+// the slices stay disjoint and 16-byte aligned).  pe / pos depend on T only and are shared.
+static Workspace slice_workspace(const Workspace& W, const AvsrEncoderConfig& c, int b0, int T, int branch) {
+  Workspace S = W;
+  const size_t r = (size_t)b0 * T, D = c.d_model, F = c.linear_units;
+  S.x += r * D; S.xn += r * D; S.hid += r * F; S.qu += r * D; S.qv += r * D; S.kk += r * D;
+  S.vt += (size_t)b0 * D * W.Tp;
+  S.ctx += r * D; S.glu += r * D; S.dw += r * D;
+  S.splitk += (size_t)kMaxSplits * r * D;
+  S.counters += (size_t)branch * kSplitCounters;
+  S.lengths += b0;
+  return S;
 }
 
 __global__ void fill_lengths_kernel(int32_t* dst, const int32_t* src, int B, int T) {
@@ -212,8 +228,19 @@ struct AuxFork {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 
+// pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
+static int compute_pos(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int T, int prec, cudaStream_t ps) {
+  const int D = c.d_model, H = c.n_heads, L = c.num_blocks;
+  AVSR_TRY(launch_sinusoid(W.pe, T, D, operand_kind(prec), ps));
+  EpiParams e{};
+  e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = prec != AVSR_PREC_FP32;
+  return run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, ps);
+}
+
+// pos_external: the caller computes the pos tables (compute_pos) and records aux->join; this body only waits for it
 static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int B, int T,
-                        const int32_t* lengths, float* taps, int prec, cudaStream_t st, const AuxFork* aux = nullptr) {
+                        const int32_t* lengths, float* taps, int prec, cudaStream_t st, const AuxFork* aux = nullptr,
+                        bool pos_external = false) {
   const int N = B * T, D = c.d_model, F = c.linear_units, H = c.n_heads, L = c.num_blocks;
   const int opk = operand_kind(prec);           // storage of every tensor that feeds a contraction
   const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
@@ -221,20 +248,16 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
 
   // split-K tile counters must be zero on entry (they re-arm themselves; this covers a first use / an aborted run)
   AVSR_CUDA_TRY(cudaMemsetAsync(W.counters, 0, kSplitCounters * sizeof(int), st));
-  // pos_emb table and linear_pos of every layer in one GEMM (embedding.py:179-183, attention.py:170)
-  cudaStream_t ps = st;
-  if (aux) {
-    AVSR_CUDA_TRY(cudaEventRecord(aux->fork, st));
-    AVSR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-    ps = aux->stream;
+  if (!pos_external) {
+    cudaStream_t ps = st;
+    if (aux) {
+      AVSR_CUDA_TRY(cudaEventRecord(aux->fork, st));
+      AVSR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+      ps = aux->stream;
+    }
+    AVSR_TRY(compute_pos(c, P, W, T, prec, ps));
+    if (aux) AVSR_CUDA_TRY(cudaEventRecord(aux->join, ps));
   }
-  AVSR_TRY(launch_sinusoid(W.pe, T, D, opk, ps));
-  {
-    EpiParams e{};
-    e.M = W.Rp; e.N = L * D; e.out = W.pos; e.H = H; e.Rp = W.Rp; e.round_out = opr;
-    AVSR_TRY(run_gemm(prec, EPI_POS, W.pe, P.pos_w_all, W.Rp, L * D, D, e, ps));
-  }
-  if (aux) AVSR_CUDA_TRY(cudaEventRecord(aux->join, ps));
   // v^T pad columns [T, Tp) must be finite (FP32 / TF32 paths; the F16 path keeps V un-transposed)
   if (W.Tp != T && prec != AVSR_PREC_F16)
     AVSR_CUDA_TRY(cudaMemsetAsync(W.vt, 0, (size_t)B * D * W.Tp * sizeof(float), st));
@@ -358,6 +381,17 @@ static int forward_impl(const AvsrEncoderConfig* cfg, const void* prepared, cons
   return AVSR_OK;
 }
 
+// How many batch slices a plan runs as concurrent graph branches.  AVSR_B200_BRANCHES overrides (1 = off).
+static int plan_branches(int B, int T, int precision) {
+  int want = 1;
+  if (const char* e = getenv("AVSR_B200_BRANCHES")) want = atoi(e);
+  if (precision != AVSR_PREC_F16 || want < 2) return 1;
+  if (want > kMaxBranches) want = kMaxBranches;
+  if (want > B) want = B;
+  while (want > 1 && (long)(B / want) * T < 256) --want;   // every slice must still feed the two-SM GEMMs (M >= 256)
+  return want;
+}
+
 }  // namespace avsr
 
 // ====================================================================== C ABI
@@ -475,19 +509,55 @@ int avsr_plan_create(const AvsrEncoderConfig* cfg, const void* prepared, int B, 
     delete p;
     return AVSR_E_CUDA;
   }
-  auto drop_aux = [&]() {
+  auto drop_aux0 = [&]() {
     cudaEventDestroy(aux.fork); cudaEventDestroy(aux.join); cudaStreamDestroy(aux.stream);
   };
-  int rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st, &aux);
-  if (rc == AVSR_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaStreamSynchronize(aux.stream) != cudaSuccess)) {
-    set_error("plan warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
-    rc = AVSR_E_CUDA;
+  // Batch slices as concurrent branches (frames of different batch elements never interact in this path): the GEMMs
+  // of one slice fill the SMs another slice's one-tile-per-cluster kernels leave idle and hide their un-overlapped
+  // prologues / epilogues.  Slice h covers batch elements [b0_h, b0_h + B_h); slice 0 runs on the caller's stream.
+  const int nbr = plan_branches(B, T, precision);
+  std::vector<cudaStream_t> bstream(nbr, st);
+  std::vector<cudaEvent_t> bdone(nbr, nullptr);
+  bool bok = true;
+  for (int h = 1; h < nbr; ++h)
+    bok = bok && cudaStreamCreateWithFlags(&bstream[h], cudaStreamNonBlocking) == cudaSuccess &&
+          cudaEventCreateWithFlags(&bdone[h], cudaEventDisableTiming) == cudaSuccess;
+  auto drop_aux = [&]() {
+    drop_aux0();
+    for (int h = 1; h < nbr; ++h) { if (bdone[h]) cudaEventDestroy(bdone[h]); if (bstream[h] != st) cudaStreamDestroy(bstream[h]); }
+  };
+  if (!bok) { set_error("plan: cannot create the branch streams"); drop_aux(); delete p; return AVSR_E_CUDA; }
+  auto run_all = [&]() -> int {
+    if (nbr == 1) return forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st, &aux);
+    AVSR_CUDA_TRY(cudaEventRecord(aux.fork, st));
+    AVSR_CUDA_TRY(cudaStreamWaitEvent(aux.stream, aux.fork, 0));
+    AVSR_TRY(compute_pos(p->cfg, p->P, p->W, T, precision, aux.stream));
+    AVSR_CUDA_TRY(cudaEventRecord(aux.join, aux.stream));
+    int b0 = 0;
+    for (int h = 0; h < nbr; ++h) {
+      const int Bh = B / nbr + (h < B % nbr ? 1 : 0);
+      if (h) AVSR_CUDA_TRY(cudaStreamWaitEvent(bstream[h], aux.fork, 0));
+      const Workspace Wh = slice_workspace(p->W, p->cfg, b0, T, h);
+      AVSR_TRY(forward_body(p->cfg, p->P, Wh, Bh, T, Wh.lengths, nullptr, precision, bstream[h], &aux, true));
+      if (h) {
+        AVSR_CUDA_TRY(cudaEventRecord(bdone[h], bstream[h]));
+        AVSR_CUDA_TRY(cudaStreamWaitEvent(st, bdone[h], 0));
+      }
+      b0 += Bh;
+    }
+    return AVSR_OK;
+  };
+  int rc = run_all();
+  if (rc == AVSR_OK) {
+    bool ok = cudaStreamSynchronize(st) == cudaSuccess && cudaStreamSynchronize(aux.stream) == cudaSuccess;
+    for (int h = 1; h < nbr; ++h) ok = ok && cudaStreamSynchronize(bstream[h]) == cudaSuccess;
+    if (!ok) { set_error("plan warm-up failed: %s", cudaGetErrorString(cudaGetLastError())); rc = AVSR_E_CUDA; }
   }
   if (rc != AVSR_OK) { drop_aux(); delete p; return rc; }
   cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); drop_aux(); delete p; return AVSR_E_CUDA; }
   const uint64_t before = g_launches.load();
-  rc = forward_body(p->cfg, p->P, p->W, B, T, W.lengths, nullptr, precision, st, &aux);   // aux joins the capture
+  rc = run_all();   // aux and the branch streams join the capture
   g_launches.store(before);  // captured launches are counted when the graph is replayed
   e = cudaStreamEndCapture(st, &p->graph);
   drop_aux();
