@@ -234,6 +234,28 @@ def test_full_size_s2_against_oracle(dev, prec):
     assert err_stats(outp, out[perm])[0] < (1e-5 if prec == "fp32" else 5e-3)
 
 
+@pytest.mark.parametrize("shape", ["S1", "S2r", "S3", "S4"])
+def test_survey_shapes_against_oracle(dev, shape):
+    """The other canonical shapes of SURVEY.md section 8 at full size (12 layers, d=768) in the default arithmetic:
+    S1 = one 100-frame utterance with mask None (configs[0]), S2r = ragged max-frames bucket (400 padded frames),
+    S3 = 16 x 100 frames, S4 = one 1600-frame utterance (13 key tiles, 3199-row rel-pos table)."""
+    from auto_avsr_b200.synthetic import SHAPES, encoder_input, encoder_state_dict
+    lengths = list(SHAPES[shape])
+    sd = encoder_state_dict(0)
+    xs = encoder_input(lengths, 768, 1234)
+    case = dict(cfg=dict(d_model=768, n_heads=12, linear_units=3072, num_blocks=12, cnn_kernel=31), sd=sd)
+    enc = _encoder(case, dev, "f16")
+    masked = shape != "S1"
+    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev) if masked else None
+    out = enc(xs.to(dev), mask)[0].cpu()
+    ref = O.encoder_forward(sd, xs.float(), lengths if masked else None, 12)
+    assert torch.isfinite(out).all()
+    mx, rms = err_stats(out, ref)
+    assert mx < TOL_ENC["f16"][0] and rms < TOL_ENC["f16"][1], (shape, mx, rms)
+    again = enc(xs.to(dev), mask)[0].cpu()
+    assert torch.equal(out, again), "graph replay must be bit-identical run to run"
+
+
 @pytest.mark.parametrize("prec", PRECS)
 def test_edge_shapes(dev, prec):
     from auto_avsr_b200 import ConformerEncoder
