@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libavsr_b200.so")
+#: AVSR_B200_LIB selects another build of the SAME library (e.g. the phase-trace build of scripts/build_trace.py);
+#: it is still this C ABI and still CUDA-only -- there is no alternative implementation to point it at.
+LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libavsr_b200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2

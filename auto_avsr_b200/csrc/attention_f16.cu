@@ -60,7 +60,11 @@ __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmP, const int32_t* __restrict__ lengths,
-                     __half* __restrict__ ctx, int T, int H) {
+                     __half* __restrict__ ctx, int T, int H
+#ifdef AVSR_TRACE
+                     , unsigned long long* trace
+#endif
+                     ) {
   extern __shared__ uint8_t ah_smem_raw[];
   const uint32_t raw = smem_u32(ah_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -80,6 +84,12 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   int L = T;
   if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }   // lengths: written before the graph, not by the predecessor
   const int nkt = (L + AH_BKV - 1) / AH_BKV;
+#ifdef AVSR_TRACE
+  // phase marks: 0 prologue done, 1 dependency resolved, 2 first S/G MMAs issued, 3 softmax sees S/G(0),
+  // 4 softmax published P(0), 5 softmax sees O(0), 6 softmax warp done with the last tile, 7 CTA drained
+  unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + AH_BARS + 96);
+  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, trace, 300, (unsigned)nkt | ((unsigned)blockIdx.z << 8));
+#endif
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQu); tma_prefetch_desc(&tmQv); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -93,7 +103,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 0);
   pdl_wait();
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -134,6 +146,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       mbar_wait(kp_full, 0);
       tc_fence_after();
       issue_scores();
+      AVSR_TRACE_MARK(true, trc, 2);
       for (int it = 0; it < nkt; ++it) {
         mbar_wait(p_full, it & 1);   // softmax consumed S/G(it) and published P(it)
         mbar_wait(v_full, it & 1);
@@ -178,6 +191,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       const int j0 = it * AH_BKV + hf * 64;       // first key this thread scores
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      AVSR_TRACE_MARK(it == 0 && threadIdx.x == 64, trc, 3);
       float s[64];   // raw (unscaled) scores of this thread's 64 keys
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -247,8 +261,10 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();        // our tcgen05.ld of S/G are complete before the MMA warp overwrites them
       mbar_arrive(p_full);
+      AVSR_TRACE_MARK(it == 0 && threadIdx.x == 64, trc, 4);
       mbar_wait(o_full, it & 1);
       tc_fence_after();
+      AVSR_TRACE_MARK(it == 0 && threadIdx.x == 64, trc, 5);
       {
         float pv[32];
         tmem_ld32(trow + TH_O + hf * 32, pv);
@@ -257,6 +273,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha, pv[d]);
       }
     }
+    AVSR_TRACE_MARK(threadIdx.x == 64, trc, 6);
     // total row sum = both halves' partial sums (same running max in both threads)
     float* slot = xch + (nkt & 1) * 256;
     slot[hf * 128 + r] = l_run;
@@ -272,6 +289,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -291,7 +309,12 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
   AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AH_BAND, 2));
   AVSR_SET_MAX_SMEM(attention_f16_kernel, AH_SMEM);
   dim3 grid(H, B, cdiv(T, AH_BQ));
+#ifdef AVSR_TRACE
+  AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H,
+              g_trace_buf);
+#else
   AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
+#endif
   return AVSR_OK;
 }
 

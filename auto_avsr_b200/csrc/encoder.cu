@@ -406,6 +406,21 @@ struct AvsrPlan {
   cudaGraphExec_t exec = nullptr;
 };
 
+#ifdef AVSR_TRACE
+namespace avsr { unsigned long long* g_trace_buf = nullptr; }
+// diagnostic build only (scripts/build_trace.py): device buffer of `words` 64-bit words, see common.cuh "phase trace"
+extern "C" int avsr_trace_set(void* device_buffer, size_t words, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!device_buffer || words < 2 + (size_t)kTraceWords) { avsr::g_trace_buf = nullptr; return AVSR_OK; }
+  const unsigned long long head[2] = {0ULL, (unsigned long long)((words - 2) / kTraceWords)};
+  AVSR_CUDA_TRY(cudaMemsetAsync(device_buffer, 0, words * 8, st));
+  AVSR_CUDA_TRY(cudaMemcpyAsync(device_buffer, head, sizeof(head), cudaMemcpyHostToDevice, st));
+  AVSR_CUDA_TRY(cudaStreamSynchronize(st));
+  avsr::g_trace_buf = reinterpret_cast<unsigned long long*>(device_buffer);
+  return AVSR_OK;
+}
+#endif
+
 extern "C" {
 
 int avsr_abi_version(void) { return AVSR_ABI_VERSION; }

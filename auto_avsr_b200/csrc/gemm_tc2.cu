@@ -111,6 +111,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * S);
+#ifdef AVSR_TRACE
+  // phase marks: 0 prologue done, 1 dependency resolved, 2 first TMA issued, 3 last TMA issued, 4 first stage full,
+  // 5 last MMA committed, 6 accumulator visible to the epilogue, 7 epilogue warp done, 8 cluster drained
+  unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + S * Cfg::kStageBytes + 192);
+  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, ep.trace, 200 + MODE, (unsigned)BNP | ((unsigned)(K / 64 / nsplit) << 16));
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
@@ -137,7 +143,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();          // both CTAs' barriers are initialised and TMEM is allocated before anyone signals a peer
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 0);
   pdl_wait();
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -154,7 +162,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (Cfg::kNSub == 2)
           tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
                           n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(s));
+        AVSR_TRACE_MARK(kb == 0, trc, 2);
       }
+      AVSR_TRACE_MARK(true, trc, 3);
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
@@ -165,6 +175,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        AVSR_TRACE_MARK(kb == 0, trc, 4);
         const uint32_t a_addr = base + s * Cfg::kStageBytes;
         const uint64_t a_desc = umma_desc_sw128(a_addr);
 #pragma unroll
@@ -177,6 +188,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
       }
       tc_commit_2sm(tmem_full_bar);        // accumulator complete: wakes both CTAs' epilogues
+      AVSR_TRACE_MARK(true, trc, 5);
     }
   } else {
     // ---------------------------------------------------------------- epilogue (both CTAs: own 128 rows)
@@ -199,6 +211,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("bar.sync 1, 256;" ::: "memory");
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    AVSR_TRACE_MARK(threadIdx.x == 64, trc, 6);
     const int mw = m0 + (int)rank * 128 + q * 32;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     if constexpr (MODE == EPI_GLU) {
@@ -344,9 +357,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   }
+  AVSR_TRACE_MARK(threadIdx.x == 64, trc, 7);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the peer may still be reading TMEM / its barriers may still receive our commits
+  AVSR_TRACE_MARK(threadIdx.x == 0, trc, 8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
@@ -358,8 +373,14 @@ static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         int tiles_n, int nsplit, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
+#ifdef AVSR_TRACE
+  EpiParams epl = ep;
+  epl.trace = g_trace_buf;
+#else
+  const EpiParams& epl = ep;
+#endif
   AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n,
-              nsplit, ep);
+              nsplit, epl);
   return AVSR_OK;
 }
 

@@ -86,6 +86,22 @@ def test_no_cpu_fallback(built):
         enc(torch.zeros(1, 8, 768), None)
 
 
+def test_missing_library_fails_loudly(built):
+    """Without the built CUDA library the package must not import (AVSR_B200_LIB points the loader at another
+    build of the same library; a path that does not exist is the 'extension missing' case)."""
+    r = subprocess.run([sys.executable, "-c", "import auto_avsr_b200._cabi"], cwd=ROOT, capture_output=True, text=True,
+                       env=dict(os.environ, AVSR_B200_LIB="/nonexistent/libavsr_b200.so"), timeout=120)
+    assert r.returncode != 0
+    assert "ImportError" in r.stderr and "no CPU / PyTorch fallback" in r.stderr
+
+
+def test_trace_hooks_are_absent_from_the_product_build(built):
+    """The phase-trace instrumentation (scripts/build_trace.py, -DAVSR_TRACE) is a separate diagnostic build."""
+    import ctypes
+    lib = ctypes.CDLL(built)
+    assert not hasattr(lib, "avsr_trace_set")
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "auto_avsr_b200")
     for dp, _, files in os.walk(pkg):
