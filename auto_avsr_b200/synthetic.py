@@ -95,6 +95,24 @@ def encoder_input(lengths: Sequence[int], d_model: int = 768, seed: int = 1234,
     return torch.randn(B, T, d_model, generator=g, dtype=torch.float64).to(dtype)
 
 
+def head_state_dict(seed: int = 0, idim: int = 512, d_model: int = 768, odim: int = 5049,
+                    dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
+    """Synthetic weights of the two Linear layers either side of the encoder in the reference's ``E2E`` model, under
+    the reference's state-dict keys: ``proj_encoder`` (e2e_asr_conformer.py:31) and ``ctc.ctc_lo`` (ctc.py:21)."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, out_f, in_f in (("proj_encoder", d_model, idim), ("ctc.ctc_lo", odim, d_model)):
+        w = (torch.rand((out_f, in_f), generator=_gen(seed, key + ".weight"), dtype=torch.float64) * 2 - 1)
+        sd[key + ".weight"] = w.mul_(1.0 / math.sqrt(in_f)).to(dtype)
+        sd[key + ".bias"] = (torch.randn((out_f,), generator=_gen(seed, key + ".bias"), dtype=torch.float64) * 0.1).to(dtype)
+    return sd
+
+
+def frontend_features(lengths: Sequence[int], idim: int = 512, seed: int = 4321,
+                      dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """(B, Tmax, idim) stand-in for the ResNet front-end's output (the input of ``proj_encoder``)."""
+    return encoder_input(lengths, idim, seed, dtype)
+
+
 #: Canonical length sets of SURVEY.md §8 (25 Hz frames).
 SHAPES: Dict[str, Sequence[int]] = {
     "S1": [100],

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict
+from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict, frontend_features, head_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -19,6 +19,18 @@ def load_case(name):
     return dict(z=z, cfg=dict(d_model=d_model, n_heads=n_heads, linear_units=linear_units,
                               num_blocks=num_blocks, cnn_kernel=cnn_kernel),
                 lengths=lengths, masked=masked, sd=sd, xs=xs)
+
+
+def load_head_case(name):
+    """Golden case of the steps either side of the encoder (oracle/make_golden_head.py)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = {k[4:]: int(z[k]) for k in z.files if k.startswith("cfg_")}
+    lengths = [int(v) for v in z["lengths"]]
+    enc_sd = encoder_state_dict(cfg["wseed"], cfg["d_model"], cfg["n_heads"], cfg["linear_units"], cfg["num_blocks"],
+                                cfg["cnn_kernel"])
+    head_sd = head_state_dict(cfg["wseed"], cfg["idim"], cfg["d_model"], cfg["odim"])
+    feats = frontend_features(lengths, cfg["idim"], cfg["xseed"])
+    return dict(z=z, cfg=cfg, lengths=lengths, masked=bool(cfg["masked"]), enc_sd=enc_sd, head_sd=head_sd, feats=feats)
 
 
 def err_stats(a, b):
