@@ -9,12 +9,18 @@ CPU or PyTorch fallback.  ``auto_avsr_b200.synthetic`` (weights / inputs generat
 __version__ = "0.1.0"
 
 _LAZY = {"ConformerEncoder", "Encoder", "EncoderLayer", "ConvolutionModule", "RelPositionMultiHeadedAttention",
-         "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding"}
+         "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "CTC", "ProjEncoder"}
 
 
 def install():
     from .install import install as _install
     _install()
+
+
+def install_head(model):
+    """Swap an already-built reference ``E2E``'s ``proj_encoder`` and ``ctc`` for the B200 drop-ins (same parameters)."""
+    from .install import install_head as _install_head
+    return _install_head(model)
 
 
 def __getattr__(name):

@@ -79,6 +79,7 @@ SIGNATURES = {
     "avsr_pointwise_glu_workspace_bytes": (_Z, [_I, _I]),
     "avsr_pointwise_glu": (_I, [_P, _P, _P, _P, _I, _I, _P, _Z, _I, _P]),
     "avsr_rel_sinusoid_table": (_I, [_P, _I, _I, _P]),
+    "avsr_log_softmax": (_I, [_P, C.c_long, _P, C.c_long, _P, _I, _I, _P]),
 }
 
 if not os.path.exists(LIB_PATH):

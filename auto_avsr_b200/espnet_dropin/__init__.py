@@ -1,6 +1,7 @@
 """Modules mirroring the reference's espnet class surface for the encoder hot path."""
 from .attention import RelPositionMultiHeadedAttention
 from .conformer_encoder import ConformerEncoder, ConvolutionModule, EncoderLayer
+from .ctc import CTC, ProjEncoder
 from .embedding import RelPositionalEncoding
 from .layer_norm import LayerNorm
 from .positionwise_feed_forward import PositionwiseFeedForward
@@ -10,4 +11,5 @@ from .repeat import MultiSequential, repeat
 Encoder = ConformerEncoder
 
 __all__ = ["ConformerEncoder", "Encoder", "EncoderLayer", "ConvolutionModule", "RelPositionMultiHeadedAttention",
-           "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "MultiSequential", "repeat"]
+           "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "MultiSequential", "repeat", "CTC",
+           "ProjEncoder"]

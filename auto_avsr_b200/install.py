@@ -38,6 +38,27 @@ def install() -> None:
         e2e.ConformerEncoder = ce.ConformerEncoder
 
 
+def install_head(model):
+    """The steps either side of the encoder.  The reference builds ``proj_encoder`` as a bare
+    ``torch.nn.Linear`` and ``ctc`` from a module it imports by name (e2e_asr_conformer.py:11, :31, :56), so instead of
+    shadowing an import this re-homes the two sub-modules of an existing ``E2E`` instance: the drop-ins take over the
+    very same ``Parameter`` objects (state dict, optimizer and checkpoint loading are unaffected)."""
+    from .espnet_dropin.ctc import CTC, ProjEncoder
+
+    old = model.proj_encoder
+    new = ProjEncoder(old.in_features, old.out_features, bias=old.bias is not None)
+    new.weight, new.bias = old.weight, old.bias
+    new.train(old.training)
+    model.proj_encoder = new
+
+    oc = model.ctc
+    nc = CTC(oc.ctc_lo.out_features, oc.ctc_lo.in_features, oc.dropout_rate, reduce=oc.reduce)
+    nc.ctc_lo.weight, nc.ctc_lo.bias = oc.ctc_lo.weight, oc.ctc_lo.bias
+    nc.train(oc.training)
+    model.ctc = nc
+    return model
+
+
 def is_installed() -> bool:
     mod = sys.modules.get(REF_ENCODER_MODULE)
     return mod is not None and mod.__name__.startswith("auto_avsr_b200")

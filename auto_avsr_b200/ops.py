@@ -100,3 +100,34 @@ def rel_sinusoid_table(T: int, d: int, device) -> torch.Tensor:
     with torch.cuda.device(device):
         check(lib.avsr_rel_sinusoid_table(pe.data_ptr(), T, d, _stream_handle(torch.device(device))))
     return pe
+
+
+def log_softmax(x: torch.Tensor, n: Optional[int] = None, want_argmax: bool = False):
+    """log_softmax over the first ``n`` entries of the last dim of ``x`` (default: all of it), fp32.  ``x`` may be a
+    padded GEMM output: its row stride is its last dimension.  Returns ``(…, n)`` log-probs, plus the int64 arg max
+    per row when ``want_argmax`` (CTC.log_softmax / CTC.argmax, ctc.py:77-93)."""
+    x = _prep(x, "x")
+    if x.dtype != torch.float32:
+        raise TypeError("log_softmax: fp32 logits expected")
+    ld = x.size(-1)
+    n = ld if n is None else int(n)
+    if not 0 < n <= ld:
+        raise ValueError(f"log_softmax: n={n} outside (0, {ld}]")
+    rows = x.numel() // ld
+    y = torch.empty(*x.shape[:-1], n, dtype=torch.float32, device=x.device)
+    best = torch.empty(x.shape[:-1], dtype=torch.int32, device=x.device) if want_argmax else None
+    with torch.cuda.device(x.device):
+        check(lib.avsr_log_softmax(x.data_ptr(), ld, y.data_ptr(), n, _ptr(best), rows, n, _stream_handle(x.device)))
+    return (y, best.long()) if want_argmax else y
+
+
+def argmax_rows(x: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+    """arg max over the first ``n`` entries of the last dim (first index on ties), int64."""
+    x = _prep(x, "x")
+    ld = x.size(-1)
+    n = ld if n is None else int(n)
+    rows = x.numel() // ld
+    best = torch.empty(x.shape[:-1], dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.avsr_log_softmax(x.data_ptr(), ld, None, 0, best.data_ptr(), rows, n, _stream_handle(x.device)))
+    return best.long()

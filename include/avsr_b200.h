@@ -169,6 +169,13 @@ int avsr_pointwise_glu(const float *x, const float *w, const float *b, float *y,
 /* pos_emb table of RelPositionalEncoding (transformer/embedding.py:139-184): (2T-1, d) fp32, row m = sinusoid(T-1-m). */
 int avsr_rel_sinusoid_table(float *pe, int T, int d, void *stream);
 
+/* ---- the step behind the encoder ------------------------------------------------------------
+ * CTC.log_softmax / CTC.argmax (espnet/nets/pytorch_backend/ctc.py:77-93) over logits that avsr_linear produced
+ * (ctc_lo: Linear(768 -> odim), ctc.py:21): y[r, 0..n) = x[r, 0..n) - logsumexp(x[r, 0..n)), argmax[r] = first index
+ * of the row maximum.  x has row stride ldx >= n (the GEMM output may be padded), y row stride ldy >= n; y or argmax
+ * may be NULL (not both). */
+int avsr_log_softmax(const float *x, long ldx, float *y, long ldy, int32_t *argmax, int rows, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

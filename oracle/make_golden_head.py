@@ -25,7 +25,7 @@ from espnet.nets.pytorch_backend.nets_utils import make_non_pad_mask  # noqa: E4
 from auto_avsr_b200.synthetic import encoder_state_dict, frontend_features, head_state_dict  # noqa: E402
 
 CASES = [
-    dict(name="head_tiny", idim=48, d_model=128, n_heads=2, linear_units=256, num_blocks=1, cnn_kernel=31, odim=37,
+    dict(name="head_tiny", idim=64, d_model=128, n_heads=2, linear_units=256, num_blocks=1, cnn_kernel=31, odim=37,
          lengths=[19, 12, 7], masked=True, wseed=31, xseed=41),
     dict(name="head_full", idim=512, d_model=768, n_heads=12, linear_units=3072, num_blocks=2, cnn_kernel=31,
          odim=5049, lengths=[11, 7], masked=True, wseed=32, xseed=42),

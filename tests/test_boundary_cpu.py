@@ -140,3 +140,64 @@ print("OK", sum(p.numel() for p in m.parameters()))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "OK 243049202" in r.stdout      # audio E2E parameter count, README.md:124-125 / BASELINE.md section 2
+
+
+# ------------------------------------------------------------------ steps either side of the encoder (8f #1)
+def test_head_dropins_keep_the_reference_state_dict_keys_and_refuse_cpu(built):
+    from auto_avsr_b200 import CTC, ProjEncoder
+    from auto_avsr_b200.synthetic import head_state_dict
+    sd = head_state_dict(3)
+    ctc = CTC(5049, 768, 0.1, reduce=True)
+    proj = ProjEncoder(512, 768)
+    ctc.load_state_dict({"ctc_lo.weight": sd["ctc.ctc_lo.weight"], "ctc_lo.bias": sd["ctc.ctc_lo.bias"]}, strict=True)
+    proj.load_state_dict({"weight": sd["proj_encoder.weight"], "bias": sd["proj_encoder.bias"]}, strict=True)
+    assert list(ctc.state_dict()) == ["ctc_lo.weight", "ctc_lo.bias"]
+    assert (ctc.reduce, ctc.ignore_id, ctc.dropout_rate, ctc.ctc_loss.reduction) == (True, -1, 0.1, "sum")
+    ctc.eval(); proj.eval()
+    for call in (lambda: ctc.log_softmax(torch.zeros(1, 3, 768)), lambda: ctc.softmax(torch.zeros(1, 3, 768)),
+                 lambda: ctc.argmax(torch.zeros(1, 3, 768)), lambda: proj(torch.zeros(1, 3, 512))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    with pytest.raises(NotImplementedError):
+        ctc(torch.zeros(1, 3, 768), torch.tensor([3]), torch.zeros(1, 2, dtype=torch.long))
+    ctc.train()
+    with pytest.raises(NotImplementedError, match="inference"):
+        ctc.log_softmax(torch.zeros(1, 3, 768))
+    # the padded copy of ctc_lo follows parameter updates
+    wp, bp = ctc._padded_params()
+    assert wp.shape == (5120, 768) and bp.shape == (5120,) and float(wp[5049:].abs().sum()) == 0.0
+    with torch.no_grad():
+        ctc.ctc_lo.weight.add_(1.0)
+    wp2, _ = ctc._padded_params()
+    assert torch.equal(wp2[:5049], ctc.ctc_lo.weight.detach()) and wp2 is not wp
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_install_head_rehomes_the_reference_modules(built):
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {REF!r})
+import torch
+from espnet.nets.pytorch_backend.ctc import CTC as RefCTC
+import auto_avsr_b200
+
+class Shell(torch.nn.Module):          # the two members E2E.__init__ builds (e2e_asr_conformer.py:31, :56)
+    def __init__(self):
+        super().__init__()
+        self.proj_encoder = torch.nn.Linear(512, 768)
+        self.ctc = RefCTC(5049, 768, 0.1, reduce=True)
+
+m = Shell().eval()
+before = {{k: v.data_ptr() for k, v in m.state_dict().items()}}
+params = {{id(p) for p in m.parameters()}}
+auto_avsr_b200.install_head(m)
+assert type(m.proj_encoder).__module__ == "auto_avsr_b200.espnet_dropin.ctc"
+assert type(m.ctc).__module__ == "auto_avsr_b200.espnet_dropin.ctc"
+after = {{k: v.data_ptr() for k, v in m.state_dict().items()}}
+assert before == after, (before.keys(), after.keys())
+assert params == {{id(p) for p in m.parameters()}}
+assert not m.ctc.training and not m.proj_encoder.training
+print("OK")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr[-2000:]
