@@ -52,6 +52,14 @@ def test_sizes_and_argument_errors_without_gpu(built):
     assert b"d_model" in _cabi.lib.avsr_last_error()
     with pytest.raises(_cabi.AvsrError):
         _cabi.check(_cabi.lib.avsr_layernorm(None, None, None, None, 4, 768, None))
+    # log-softmax entry: NULL input, row stride shorter than the row, and the empty batch (a no-op, no launch)
+    with pytest.raises(_cabi.AvsrError):
+        _cabi.check(_cabi.lib.avsr_log_softmax(None, 8, None, 8, None, 1, 8, None))
+    with pytest.raises(_cabi.AvsrError, match="ldx"):
+        _cabi.check(_cabi.lib.avsr_log_softmax(0x1000, 4, 0x2000, 8, None, 1, 8, None))
+    before = _cabi.launch_count()
+    _cabi.check(_cabi.lib.avsr_log_softmax(0x1000, 8, 0x2000, 8, None, 0, 8, None))
+    assert _cabi.launch_count() == before
 
 
 def test_state_dict_contract(built, golden_dir):
