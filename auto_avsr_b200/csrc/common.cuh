@@ -306,6 +306,9 @@ int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, c
 // deferred split-K (gemm_tc2.cu): plan returns 1 and fills bnp / nsplit when the shape qualifies; the GEMM writes
 // partial[s][M][N] (raw fp32 k-slice sums) and the consuming LayerNorm finishes the residual update (LnParts)
 int gemm_tc2_splitk_plan(int M, int N, int K, int* bnp, int* nsplit);
+// true while the caller guarantees that B operands are prepared weights no kernel of the stream writes (the encoder
+// forward): lets the experimental AVSR_B200_PREB=1 variant fetch weights before griddepcontrol.wait
+extern thread_local bool g_tc2_weights_static;
 int gemm_tc2_splitk(const void* A, const void* Bw, int M, int N, int K, float* partial, int bnp, int nsplit,
                     cudaStream_t st);
 

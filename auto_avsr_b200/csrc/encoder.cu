@@ -245,6 +245,10 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
   const int opk = operand_kind(prec);           // storage of every tensor that feeds a contraction
   const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
   const size_t stage_bytes = (size_t)N * D * sizeof(float);
+  struct StaticWeights {                        // every GEMM below reads prepared weights (see g_tc2_weights_static)
+    StaticWeights() { g_tc2_weights_static = true; }
+    ~StaticWeights() { g_tc2_weights_static = false; }
+  } static_weights_scope;
 
   // split-K tile counters must be zero on entry (they re-arm themselves; this covers a first use / an aborted run)
   AVSR_CUDA_TRY(cudaMemsetAsync(W.counters, 0, kSplitCounters * sizeof(int), st));

@@ -93,7 +93,10 @@ struct T2Cfg {
 
 // RELU / RESID are compile-time: a predicated-off instruction still takes an issue slot, and this epilogue is not
 // overlapped with anything (one tile per cluster).
-template <int MODE, int BNP, bool RELU, bool RESID>
+// PREB (experimental, AVSR_B200_PREB=1, prepared weights only): the B operand (weights) does not depend on the
+// predecessor kernel, so the producer fills the B halves of the first stages BEFORE griddepcontrol.wait; after the
+// wait only the A tiles (just written by the predecessor, L2-resident) are still to come.
+template <int MODE, int BNP, bool RELU, bool RESID, bool PREB = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmB1, int K, int tiles_n, int nsplit, EpiParams ep) {
@@ -144,6 +147,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 0);
+  if constexpr (PREB) {
+    if (warp == 0 && lane == 0) {
+      const int npre = nkb < S ? nkb : S;      // every stage is free on entry: no empty-barrier wait needed
+      for (int kb = 0; kb < npre; ++kb) {
+        if (rank == 0) mbar_expect_tx(full_bar(kb), 2 * Cfg::kStageBytes);
+        const uint32_t dst = base + kb * Cfg::kStageBytes;
+        const int kc = (kb0 + kb) * KE;
+        tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kc, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(kb));
+        if constexpr (Cfg::kNSub == 2)
+          tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
+                          n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(kb));
+      }
+    }
+  }
   pdl_wait();
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
 
@@ -152,6 +169,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
+        if constexpr (PREB) {
+          if (kb < S) {                                                   // expect_tx + B already issued before the wait
+            tma_load_2d_2sm(base + s * Cfg::kStageBytes, &tmA, (kb0 + kb) * KE, m0 + (int)rank * 128, full_bar(s));
+            AVSR_TRACE_MARK(kb == 0, trc, 2);
+            continue;
+          }
+        }
         mbar_wait(empty_bar(s), ph ^ 1);                                  // own stage free (leader's commit, multicast)
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes); // bytes of BOTH CTAs land on the leader's barrier
         const uint32_t dst = base + s * Cfg::kStageBytes;
@@ -368,6 +392,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// set by encoder.cu around the forward schedule: B operands are prepared weights nobody writes during the forward
+thread_local bool g_tc2_weights_static = false;
+static bool preb_enabled() {
+  static const bool on = [] { const char* e = getenv("AVSR_B200_PREB"); return e && e[0] == '1'; }();
+  return on && g_tc2_weights_static && pdl_enabled();
+}
+
 template <int MODE, int BNP, bool RELU, bool RESID>
 static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, int grid, int K,
                         int tiles_n, int nsplit, const EpiParams& ep, cudaStream_t st) {
@@ -379,6 +410,12 @@ static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 #else
   const EpiParams& epl = ep;
 #endif
+  if (preb_enabled()) {
+    AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), Cfg::kSmem);
+    AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K,
+                tiles_n, nsplit, epl);
+    return AVSR_OK;
+  }
   AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n,
               nsplit, epl);
   return AVSR_OK;
