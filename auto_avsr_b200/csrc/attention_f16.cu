@@ -60,11 +60,7 @@ __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_constant__ CUtensorMap tmQv,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmP, const int32_t* __restrict__ lengths,
-                     __half* __restrict__ ctx, int T, int H
-#ifdef AVSR_TRACE
-                     , unsigned long long* trace
-#endif
-                     ) {
+                     __half* __restrict__ ctx, int T, int H) {
   extern __shared__ uint8_t ah_smem_raw[];
   const uint32_t raw = smem_u32(ah_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -88,7 +84,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   // phase marks: 0 prologue done, 1 dependency resolved, 2 first S/G MMAs issued, 3 softmax sees S/G(0),
   // 4 softmax published P(0), 5 softmax sees O(0), 6 softmax warp done with the last tile, 7 CTA drained
   unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + AH_BARS + 96);
-  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, trace, 300, (unsigned)nkt | ((unsigned)blockIdx.z << 8));
+  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, 300, (unsigned)nkt | ((unsigned)blockIdx.z << 8));
 #endif
 
   if (threadIdx.x == 0) {
@@ -106,6 +102,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 0);
   pdl_wait();
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
+  AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -290,11 +287,14 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   tc_fence_before();
   __syncthreads();
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 7);
+  AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 11);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
 }
+
+AVSR_TRACE_DEFINE_BIND(trace_bind_attention_f16)
 
 int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vv, const __half* pos,
                   const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st) {
@@ -312,12 +312,7 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
   AVSR_TRY(make_tmap_3d(&tmP, pos, (uint64_t)H, (uint64_t)Rp, 64, 64, (uint64_t)Rp * 64, AH_BAND, 2));
   AVSR_SET_MAX_SMEM(attention_f16_kernel, AH_SMEM);
   dim3 grid(H, B, cdiv(T, AH_BQ));
-#ifdef AVSR_TRACE
-  AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H,
-              g_trace_buf);
-#else
   AVSR_LAUNCH(attention_f16_kernel, grid, AH_THREADS, AH_SMEM, st, tmQu, tmQv, tmK, tmV, tmP, lengths, ctx, T, H);
-#endif
   return AVSR_OK;
 }
 

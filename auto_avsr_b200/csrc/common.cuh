@@ -203,42 +203,65 @@ struct EpiParams {
   void* qv;
   void* kk;
   void* vt;
-#ifdef AVSR_TRACE
-  unsigned long long* trace;   // phase trace buffer of the diagnostic build (see "phase trace" below); may be null
-#endif
 };
 
 // ---------------------------------------------------------------- phase trace (diagnostic build only)
 // scripts/build_trace.py compiles the library with -DAVSR_TRACE into libavsr_b200_trace.so; the product build does
 // not contain any of this.  Buffer layout (64-bit words): [0] = records used, [1] = record capacity, then records of
 // kTraceWords words: [0] kernel id, [1] blockIdx.x | aux << 32, [2] SM id, [3] %globaltimer at open,
-// [4 + s] = clock64() at phase mark s.  One record per CTA; marks are written by whichever thread reaches the phase.
+// [4 + s] = clock64() at phase mark s (s < 10), [14] / [15] = %globaltimer when the dependency resolved / the CTA was done.
+// One record per CTA; marks are written by whichever thread reaches the phase.
 #ifdef AVSR_TRACE
 constexpr int kTraceWords = 16;
-extern unsigned long long* g_trace_buf;     // host copy of the device buffer pointer (encoder.cu: avsr_trace_set)
-__device__ __forceinline__ unsigned long long* trace_open(unsigned long long* trace, int kernel_id, unsigned aux) {
+// Every translation unit has its own copy of the buffer pointer (no relocatable device code in this build); each
+// .cu defines a binder with AVSR_TRACE_DEFINE_BIND and avsr_trace_set (encoder.cu) calls all of them.  The kernels
+// read the pointer at run time, so a CUDA graph captured before avsr_trace_set still traces.
+static __device__ unsigned long long* d_trace_buf;
+#define AVSR_TRACE_DEFINE_BIND(name)                                                         \
+  int name(unsigned long long* p) {                                                          \
+    return cudaMemcpyToSymbol(::avsr::d_trace_buf, &p, sizeof p) == cudaSuccess ? 0 : 1;     \
+  }
+__device__ __forceinline__ unsigned long long trace_globaltimer() {
+  unsigned long long gt;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+  return gt;
+}
+__device__ __forceinline__ unsigned long long* trace_open(int kernel_id, unsigned aux) {
+  unsigned long long* trace = d_trace_buf;
   if (!trace) return nullptr;
   const unsigned long long r = atomicAdd(trace, 1ULL);
   if (r >= trace[1]) return nullptr;
   unsigned long long* rec = trace + 2 + r * kTraceWords;
   unsigned smid;
-  unsigned long long gt;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
   rec[0] = (unsigned long long)kernel_id;
   rec[1] = (unsigned long long)blockIdx.x | ((unsigned long long)aux << 32);
   rec[2] = smid;
-  rec[3] = gt;
+  rec[3] = trace_globaltimer();
   return rec;
 }
 __device__ __forceinline__ void trace_mark(unsigned long long* rec, int slot) {
   if (rec) rec[4 + slot] = (unsigned long long)clock64();
 }
-#define AVSR_TRACE_OPEN(slot_ptr, trace, id, aux) do { *(slot_ptr) = ::avsr::trace_open(trace, id, aux); } while (0)
+// globaltimer stamps for the launch timeline: slot 10 = dependency resolved (after griddepcontrol.wait), 11 = CTA done
+__device__ __forceinline__ void trace_stamp(unsigned long long* rec, int slot) {
+  if (rec) rec[4 + slot] = trace_globaltimer();
+}
+#define AVSR_TRACE_OPEN(slot_ptr, id, aux) do { *(slot_ptr) = ::avsr::trace_open(id, aux); } while (0)
 #define AVSR_TRACE_MARK(cond, slot_ptr, s) do { if (cond) ::avsr::trace_mark(*(slot_ptr), s); } while (0)
+#define AVSR_TRACE_STAMP(cond, slot_ptr, s) do { if (cond) ::avsr::trace_stamp(*(slot_ptr), s); } while (0)
+// simple kernels (no shared slot): thread 0 of the CTA keeps the record pointer in a register
+#define AVSR_TSPAN_OPEN(id, aux) unsigned long long* _tsp = threadIdx.x == 0 ? ::avsr::trace_open(id, aux) : nullptr
+#define AVSR_TSPAN_DEP() ::avsr::trace_stamp(_tsp, 10)
+#define AVSR_TSPAN_CLOSE() ::avsr::trace_stamp(_tsp, 11)
 #else
-#define AVSR_TRACE_OPEN(slot_ptr, trace, id, aux) do { } while (0)
+#define AVSR_TRACE_DEFINE_BIND(name)
+#define AVSR_TRACE_OPEN(slot_ptr, id, aux) do { } while (0)
 #define AVSR_TRACE_MARK(cond, slot_ptr, s) do { } while (0)
+#define AVSR_TRACE_STAMP(cond, slot_ptr, s) do { } while (0)
+#define AVSR_TSPAN_OPEN(id, aux) do { } while (0)
+#define AVSR_TSPAN_DEP() do { } while (0)
+#define AVSR_TSPAN_CLOSE() do { } while (0)
 #endif
 
 // scalar store of one operand-or-fp32 value: `operand` says the destination is TOp-typed (rounded), else plain fp32

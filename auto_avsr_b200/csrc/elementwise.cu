@@ -10,13 +10,18 @@ namespace avsr {
 // ------------------------------------------------------------------ embed: x = xs * sqrt(d)   (embedding.py:178)
 __global__ void embed_scale_kernel(const float4* __restrict__ xs, float4* __restrict__ x, long n4, float scale) {
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(130, 0);
   pdl_wait();
+  AVSR_TSPAN_DEP();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 v = xs[i];
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     x[i] = v;
   }
+  AVSR_TSPAN_CLOSE();
 }
+
+AVSR_TRACE_DEFINE_BIND(trace_bind_elementwise)
 
 int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStream_t st) {
   AVSR_REQUIRE(n % 4 == 0, "embed: element count %ld not a multiple of 4", n);
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
                                                         const float* __restrict__ beta, void* y,
                                                         int rows, int d, int out_kind, LnParts pp) {
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(100, NP);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
     if (c < nvec) { gg[i] = g4[c]; bb[i] = b4[c]; }
   }
   pdl_wait();
+  AVSR_TSPAN_DEP();
   float4 v[kLnMaxVec];
   float s = 0.f;
 #pragma unroll
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may al
       store_kind4(y, (long)warp * d + 4 * c, out_kind, o.x, o.y, o.z, o.w);
     }
   }
+  AVSR_TSPAN_CLOSE();
 }
 
 // Two chained LayerNorms in one pass over the row: y1 = LN(x; g1, b1) (fp32, may alias x) and
@@ -128,6 +136,7 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may a
                                                          void* __restrict__ y2, int rows, int d, int out_kind,
                                                          LnParts pp) {
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(110, NP);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may a
     if (c < nvec) { gg[i] = g14[c]; bb[i] = b14[c]; }
   }
   pdl_wait();
+  AVSR_TSPAN_DEP();
   const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
   float4 v[kLnMaxVec];
   float s = 0.f;
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may a
                   (v[i].y - mean) * rstd * gg[i].y + bb[i].y, (v[i].z - mean) * rstd * gg[i].z + bb[i].z,
                   (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
   }
+  AVSR_TSPAN_CLOSE();
 }
 
 int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
@@ -246,7 +257,9 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* y, in
 // argument an fp32 product; sinf/cosf here take the full-range (non fast-math) path.
 __global__ void sinusoid_kernel(void* __restrict__ pe, int T, int d, int out_kind) {
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(140, 0);
   pdl_wait();
+  AVSR_TSPAN_DEP();
   const int half = d >> 1;
   const long total = (long)(2 * T - 1) * half;
   const float step = (float)(-(log(10000.0) / (double)d));
@@ -267,6 +280,7 @@ __global__ void sinusoid_kernel(void* __restrict__ pe, int T, int d, int out_kin
       *reinterpret_cast<float2*>(reinterpret_cast<float*>(pe) + idx) = make_float2(s, co);
     }
   }
+  AVSR_TSPAN_CLOSE();
 }
 
 int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st) {
@@ -322,6 +336,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
                                                                     int T, int C, int k_runtime, int out_kind) {
   extern __shared__ float4 dw_smem[];
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(120, 0);
   const int Kt = K > 0 ? K : k_runtime;
   const int rows_in = kDwTT + Kt - 1;
   float4* in_s = dw_smem;                          // [rows_in][16]
@@ -342,6 +357,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
     w_s[i] = v;
   }
   pdl_wait();
+  AVSR_TSPAN_DEP();
   {
     const int total = rows_in * (kDwCh / 4);
     for (int i0 = tid; i0 < total; i0 += 4 * kDwThreads) {   // 4 independent 16-byte loads in flight per thread
@@ -386,6 +402,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
     }
     store_kind4(y, ((long)b * T + t) * C + c, out_kind, o.x, o.y, o.z, o.w);
   }
+  AVSR_TSPAN_CLOSE();
 }
 
 int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, void* y, int B,

@@ -411,16 +411,28 @@ struct AvsrPlan {
 };
 
 #ifdef AVSR_TRACE
-namespace avsr { unsigned long long* g_trace_buf = nullptr; }
+namespace avsr {
+int trace_bind_gemm_tc2(unsigned long long*);
+int trace_bind_attention_f16(unsigned long long*);
+int trace_bind_elementwise(unsigned long long*);
+int trace_bind_gemm_tc(unsigned long long*);
+static int trace_bind_all(unsigned long long* p) {
+  return trace_bind_gemm_tc2(p) | trace_bind_attention_f16(p) | trace_bind_elementwise(p) | trace_bind_gemm_tc(p);
+}
+}
 // diagnostic build only (scripts/build_trace.py): device buffer of `words` 64-bit words, see common.cuh "phase trace"
 extern "C" int avsr_trace_set(void* device_buffer, size_t words, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!device_buffer || words < 2 + (size_t)kTraceWords) { avsr::g_trace_buf = nullptr; return AVSR_OK; }
+  if (!device_buffer || words < 2 + (size_t)kTraceWords) {
+    AVSR_CUDA_TRY(cudaDeviceSynchronize());
+    AVSR_REQUIRE(avsr::trace_bind_all(nullptr) == 0, "trace: cannot unbind");
+    return AVSR_OK;
+  }
   const unsigned long long head[2] = {0ULL, (unsigned long long)((words - 2) / kTraceWords)};
   AVSR_CUDA_TRY(cudaMemsetAsync(device_buffer, 0, words * 8, st));
   AVSR_CUDA_TRY(cudaMemcpyAsync(device_buffer, head, sizeof(head), cudaMemcpyHostToDevice, st));
   AVSR_CUDA_TRY(cudaStreamSynchronize(st));
-  avsr::g_trace_buf = reinterpret_cast<unsigned long long*>(device_buffer);
+  AVSR_REQUIRE(avsr::trace_bind_all(reinterpret_cast<unsigned long long*>(device_buffer)) == 0, "trace: cannot bind");
   return AVSR_OK;
 }
 #endif

@@ -143,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_items = total_tiles * splits;
 
   pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(400 + MODE, (unsigned)BN | ((unsigned)MSUB << 16));
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -156,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  AVSR_TSPAN_DEP();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -481,11 +483,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  AVSR_TSPAN_CLOSE();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
+
+AVSR_TRACE_DEFINE_BIND(trace_bind_gemm_tc)
 
 static int num_sms() {
   static int n = 0;

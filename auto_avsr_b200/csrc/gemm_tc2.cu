@@ -118,7 +118,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // phase marks: 0 prologue done, 1 dependency resolved, 2 first TMA issued, 3 last TMA issued, 4 first stage full,
   // 5 last MMA committed, 6 accumulator visible to the epilogue, 7 epilogue warp done, 8 cluster drained
   unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + S * Cfg::kStageBytes + 192);
-  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, ep.trace, 200 + MODE, (unsigned)BNP | ((unsigned)(K / 64 / nsplit) << 16));
+  if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, 200 + MODE, (unsigned)BNP | ((unsigned)(K / 64 / nsplit) << 16));
 #endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -163,6 +163,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   pdl_wait();
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
+  AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -386,11 +387,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   cluster_sync_all();          // the peer may still be reading TMEM / its barriers may still receive our commits
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 8);
+  AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 11);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
   }
 }
+
+AVSR_TRACE_DEFINE_BIND(trace_bind_gemm_tc2)
 
 // set by encoder.cu around the forward schedule: B operands are prepared weights nobody writes during the forward
 thread_local bool g_tc2_weights_static = false;
@@ -404,12 +408,7 @@ static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                         int tiles_n, int nsplit, const EpiParams& ep, cudaStream_t st) {
   using Cfg = T2Cfg<BNP>;
   AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
-#ifdef AVSR_TRACE
-  EpiParams epl = ep;
-  epl.trace = g_trace_buf;
-#else
   const EpiParams& epl = ep;
-#endif
   if (preb_enabled()) {
     AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), Cfg::kSmem);
     AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K,
