@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libav
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class AvsrError(RuntimeError):
@@ -65,6 +65,7 @@ SIGNATURES = {
     "avsr_prepare_weights": (_I, [_CFG, C.POINTER(LayerParams), _P, _P, _P, _Z, _I, _P]),
     "avsr_workspace_bytes": (_Z, [_CFG, _I, _I]),
     "avsr_encoder_forward": (_I, [_CFG, _P, _P, _P, _I, _I, _P, _P, _Z, _I, _P]),
+    "avsr_encoder_forward_checked": (_I, [_CFG, _P, _P, _P, _I, _I, _P, _P, _Z, _I, _P, _P]),
     "avsr_encoder_forward_taps": (_I, [_CFG, _P, _P, _P, _I, _I, _P, _P, _P, _Z, _I, _P]),
     "avsr_plan_create": (_I, [_CFG, _P, _I, _I, _P, _Z, _I, _P, C.POINTER(_P)]),
     "avsr_plan_forward": (_I, [_P, _P, _P, _P, _P]),

@@ -300,9 +300,6 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
                   const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st) {
   AVSR_REQUIRE(Rp >= 2 * T - 1, "attention_f16: bad Rp=%d for T=%d", Rp, T);
   if (B <= 0 || T <= 0) return AVSR_OK;
-  // AVSR_B200_ATTN=x4: the experimental 16-softmax-warp variant (attention_f16x.cu); default = this file's kernel
-  static const bool x4 = [] { const char* e = getenv("AVSR_B200_ATTN"); return e && e[0] == 'x' && e[1] == '4'; }();
-  if (x4) return attention_f16x(qu, qv, kk, vv, pos, lengths, ctx, B, T, H, Rp, st);
   CUtensorMap tmQu, tmQv, tmK, tmV, tmP;
   const uint64_t rows = (uint64_t)B * H * T;
   AVSR_TRY(make_tmap_2d(&tmQu, qu, rows, 64, 64, AH_BQ, 2));

@@ -194,6 +194,36 @@ __global__ void fill_lengths_kernel(int32_t* dst, const int32_t* src, int B, int
   if (i < B) dst[i] = src ? src[i] : T;
 }
 
+// ------------------------------------------------------------------ saturation check (diagnostic forward)
+// fp16 operand stores saturate (cvt.rn.satfinite, common.cuh): a value beyond +-65504 becomes +-65504 silently.  The
+// checked forward (avsr_encoder_forward_checked) scans every operand tensor right after its producer and counts the
+// elements that sit AT the saturation value (or are NaN): non-zero means the fp16 path left its range for these
+// weights / inputs and the caller must fall back to tf32 / fp32 precision -- the drop-in raises (engine.py).
+__global__ void count_saturated_kernel(const uint4* __restrict__ p, long n16, unsigned long long* count) {
+  unsigned local = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      local += ((w[k] & 0x7fffu) >= 0x7bffu) ? 1u : 0u;
+      local += (((w[k] >> 16) & 0x7fffu) >= 0x7bffu) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+static int count_saturated(const void* halfs, size_t nelems, unsigned long long* count, cudaStream_t st) {
+  if (!count || nelems == 0) return AVSR_OK;
+  AVSR_REQUIRE(nelems % 8 == 0 && (reinterpret_cast<uintptr_t>(halfs) & 15) == 0, "saturation scan: unaligned buffer");
+  int blocks = (int)((nelems / 8 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_saturated_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(halfs), (long)(nelems / 8), count);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
 // ------------------------------------------------------------------ forward schedule
 static EpiParams epi_linear(int M, int N, const float* bias, void* out, const float* resid, float alpha, int relu,
                             int round_out) {
@@ -240,11 +270,13 @@ static int compute_pos(const AvsrEncoderConfig& c, const Prepared& P, const Work
 // pos_external: the caller computes the pos tables (compute_pos) and records aux->join; this body only waits for it
 static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Workspace& W, int B, int T,
                         const int32_t* lengths, float* taps, int prec, cudaStream_t st, const AuxFork* aux = nullptr,
-                        bool pos_external = false) {
+                        bool pos_external = false, unsigned long long* sat = nullptr) {
   const int N = B * T, D = c.d_model, F = c.linear_units, H = c.n_heads, L = c.num_blocks;
   const int opk = operand_kind(prec);           // storage of every tensor that feeds a contraction
   const int opr = prec != AVSR_PREC_FP32;       // "destination is operand-typed" flag of the epilogues
   const size_t stage_bytes = (size_t)N * D * sizeof(float);
+  if (prec != AVSR_PREC_F16) sat = nullptr;     // only the fp16 operand storage saturates
+  auto chk = [&](const void* buf, size_t nelems) -> int { return count_saturated(buf, nelems, sat, st); };
   struct StaticWeights {                        // every GEMM below reads prepared weights (see g_tc2_weights_static)
     StaticWeights() { g_tc2_weights_static = true; }
     ~StaticWeights() { g_tc2_weights_static = false; }
@@ -286,7 +318,9 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     // (1) macaron FFN: x += 0.5 * w2(relu(w1 LN(x)))                         conformer_encoder.py:110-116
     // (for l > 0 the norm_ff_macaron output was produced together with the previous layer's norm_final)
     if (l == 0) AVSR_TRY(launch_layernorm(W.x, w.ln_ffm_w, w.ln_ffm_b, W.xn, N, D, opk, st));
+    AVSR_TRY(chk(W.xn, (size_t)N * D));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ffm_w1, N, F, D, epi_linear(N, F, w.ffm_b1, W.hid, nullptr, 0.f, 1, opr), st));
+    AVSR_TRY(chk(W.hid, (size_t)N * F));
     if (w2_defer) {
       AVSR_TRY(gemm_tc2_splitk(W.hid, w.ffm_w2, N, D, F, W.splitk, w2_bnp, w2_split, st));
     } else {
@@ -297,6 +331,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
     {
       const LnParts pp = w2_parts(w.ffm_b2, W.x);
       AVSR_TRY(launch_layernorm(W.x, w.ln_mha_w, w.ln_mha_b, W.xn, N, D, opk, st, w2_defer ? &pp : nullptr));
+      AVSR_TRY(chk(W.xn, (size_t)N * D));
     }
     {
       EpiParams e{};
@@ -315,6 +350,9 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       }
     }
     if (l == 0 && aux) AVSR_CUDA_TRY(cudaStreamWaitEvent(st, aux->join, 0));   // the pos tables are ready
+    AVSR_TRY(chk(W.qu, (size_t)N * D)); AVSR_TRY(chk(W.qv, (size_t)N * D));
+    AVSR_TRY(chk(W.kk, (size_t)N * D)); AVSR_TRY(chk(W.vt, (size_t)N * D));
+    if (l == 0) AVSR_TRY(chk(W.pos, (size_t)L * W.Rp * D / 8 * 8));
     {
       const void* pos_l = op_offset(W.pos, (size_t)l * H * W.Rp * kHeadDim, prec);
       if (prec == AVSR_PREC_F16)
@@ -325,21 +363,26 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       else
         AVSR_TRY(attention_simt(W.qu, W.qv, W.kk, W.vt, (const float*)pos_l, lengths, W.ctx, B, T, H, W.Tp, W.Rp, 0, st));
     }
+    AVSR_TRY(chk(W.ctx, (size_t)N * D));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.ctx, w.out_w, N, D, D, epi_resid(N, D, w.out_b, W.x, 1.0f, W.splitk, W.counters), st));
     AVSR_TRY(tap(1));
     // (3) conv module: x += pw2(silu(bn(dw(glu(pw1 LN(x))))))                 conformer_encoder.py:145-151, :30-35
     AVSR_TRY(launch_layernorm(W.x, w.ln_conv_w, w.ln_conv_b, W.xn, N, D, opk, st));
+    AVSR_TRY(chk(W.xn, (size_t)N * D));
     {
       EpiParams e{};
       e.M = N; e.N = 2 * D; e.bias = w.pw1_b; e.out = W.glu; e.ldo = D;
       AVSR_TRY(run_gemm(prec, EPI_GLU, W.xn, w.pw1_w, N, 2 * D, D, e, st));
     }
     AVSR_TRY(launch_dwconv_bn_silu(W.glu, w.dw_wt, w.dw_scale, w.dw_shift, W.dw, B, T, D, c.cnn_kernel, opk, st));
+    AVSR_TRY(chk(W.dw, (size_t)N * D));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.dw, w.pw2_w, N, D, D, epi_resid(N, D, w.pw2_b, W.x, 1.0f, W.splitk, W.counters), st));
     AVSR_TRY(tap(2));
     // (4) FFN: x += 0.5 * w2(relu(w1 LN(x)))                                  conformer_encoder.py:154-159
     AVSR_TRY(launch_layernorm(W.x, w.ln_ff_w, w.ln_ff_b, W.xn, N, D, opk, st));
+    AVSR_TRY(chk(W.xn, (size_t)N * D));
     AVSR_TRY(run_gemm(prec, EPI_LINEAR, W.xn, w.ff_w1, N, F, D, epi_linear(N, F, w.ff_b1, W.hid, nullptr, 0.f, 1, opr), st));
+    AVSR_TRY(chk(W.hid, (size_t)N * F));
     if (w2_defer) {
       AVSR_TRY(gemm_tc2_splitk(W.hid, w.ff_w2, N, D, F, W.splitk, w2_bnp, w2_split, st));
     } else {
@@ -354,6 +397,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
       if (l + 1 < L) {
         const LayerPrep& nx = P.layers[l + 1];
         AVSR_TRY(launch_layernorm2(W.x, w.ln_fin_w, w.ln_fin_b, nx.ln_ffm_w, nx.ln_ffm_b, W.x, W.xn, N, D, opk, st, ppp));
+        // (the next iteration's first check covers this xn)
       } else {
         AVSR_TRY(launch_layernorm(W.x, w.ln_fin_w, w.ln_fin_b, W.x, N, D, OP_F32, st, ppp));
       }
@@ -365,7 +409,7 @@ static int forward_body(const AvsrEncoderConfig& c, const Prepared& P, const Wor
 
 static int forward_impl(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs, const int32_t* lengths,
                         int B, int T, float* out, float* taps, void* workspace, size_t workspace_bytes, int precision,
-                        void* stream) {
+                        void* stream, unsigned long long* sat = nullptr) {
   AVSR_TRY(check_cfg(cfg));
   AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
   AVSR_REQUIRE(B >= 0 && T >= 0, "bad B=%d T=%d", B, T);
@@ -380,7 +424,8 @@ static int forward_impl(const AvsrEncoderConfig* cfg, const void* prepared, cons
   Prepared P = layout_prepared(*cfg, const_cast<void*>(prepared));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   AVSR_TRY(launch_embed_scale(xs, W.x, (long)B * T * cfg->d_model, sqrtf((float)cfg->d_model), st));
-  AVSR_TRY(forward_body(*cfg, P, W, B, T, lengths, taps, precision, st));
+  if (sat) AVSR_CUDA_TRY(cudaMemsetAsync(sat, 0, sizeof(unsigned long long), st));
+  AVSR_TRY(forward_body(*cfg, P, W, B, T, lengths, taps, precision, st, nullptr, false, sat));
   AVSR_TRY(launch_layernorm(W.x, P.after_w, P.after_b, out, B * T, cfg->d_model, 0, st));
   return AVSR_OK;
 }
@@ -506,6 +551,14 @@ int avsr_encoder_forward(const AvsrEncoderConfig* cfg, const void* prepared, con
                          int B, int T, float* out, void* workspace, size_t workspace_bytes, int precision,
                          void* stream) {
   return forward_impl(cfg, prepared, xs, lengths, B, T, out, nullptr, workspace, workspace_bytes, precision, stream);
+}
+
+int avsr_encoder_forward_checked(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs,
+                                 const int32_t* lengths, int B, int T, float* out, void* workspace,
+                                 size_t workspace_bytes, int precision, uint64_t* saturated, void* stream) {
+  AVSR_REQUIRE(saturated != nullptr, "saturated counter is NULL");
+  return forward_impl(cfg, prepared, xs, lengths, B, T, out, nullptr, workspace, workspace_bytes, precision, stream,
+                      reinterpret_cast<unsigned long long*>(saturated));
 }
 
 int avsr_encoder_forward_taps(const AvsrEncoderConfig* cfg, const void* prepared, const float* xs,

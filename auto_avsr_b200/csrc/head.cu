@@ -21,7 +21,7 @@ __device__ __forceinline__ void ms_push(MaxSum& a, float x, int idx) {
     a.m = x;
     a.i = idx;
   } else {
-    a.s += __expf(x - a.m);
+    a.s += (x == -INFINITY) ? 0.f : __expf(x - a.m);   // x = m = -inf would give exp(nan); F.log_softmax ignores -inf logits
   }
 }
 

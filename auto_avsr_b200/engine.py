@@ -36,10 +36,21 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
         raise TypeError(f"{what}: expected float32, got {t.dtype}")
 
 
-class EncoderEngine:
-    """Runs ConformerEncoder.forward (eval) for one parameter set on one device."""
+class SaturationError(OverflowError):
+    """The fp16 operand path left its range (+-65504) for these weights / inputs: use precision "tf32" or "fp32"."""
 
-    MAX_PLANS = 8
+
+class EncoderEngine:
+    """Runs ConformerEncoder.forward (eval) for one parameter set on one device.
+
+    Shape policy (the reference's eval path feeds B=1 with a different T per utterance, lightning.py:72): a (B, T)
+    shape runs on direct launches -- one growable workspace per device, no capture cost -- until it has been seen
+    ``graph_after`` times; only then a CUDA-graph plan (own ~85 KB/frame workspace, ~190-node capture) is built for it.
+    Plans live in an LRU of ``MAX_PLANS`` (env AVSR_B200_MAX_PLANS).  Fixed-shape loops (training buckets, bench)
+    reach the graph after ``graph_after - 1`` calls; ``graph_after=1`` captures at first sight."""
+
+    MAX_PLANS = int(os.environ.get("AVSR_B200_MAX_PLANS", "16"))
+    GRAPH_AFTER = int(os.environ.get("AVSR_B200_GRAPH_AFTER", "3"))
 
     def __init__(self, d_model: int, n_heads: int, linear_units: int, num_blocks: int, cnn_kernel: int):
         self.cfg = EncoderConfig(d_model, n_heads, linear_units, num_blocks, cnn_kernel)
@@ -50,7 +61,11 @@ class EncoderEngine:
         self._prepared: Dict[Tuple[int, int], torch.Tensor] = {}      # (device index, precision) -> buffer
         self._workspaces: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
         self._plans: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._seen: "OrderedDict[tuple, int]" = OrderedDict()        # shape key -> times seen (bounded)
         self._capture_stream: Dict[int, torch.cuda.Stream] = {}
+        self._sat: Dict[int, torch.Tensor] = {}
+        self.graph_after = self.GRAPH_AFTER
+        self.stats = {"direct": 0, "graph": 0, "plans_built": 0}
 
     # ---- weights -------------------------------------------------------------------------------
     def invalidate(self) -> None:
@@ -85,6 +100,9 @@ class EncoderEngine:
             for field, suffix in LAYER_FIELDS:
                 t = state[f"encoders.{l}.{suffix}"]
                 require_cuda(t, suffix)
+                if t.device != device:
+                    raise RuntimeError(f"encoder parameter {suffix} (layer {l}) lives on {t.device} but the input is on "
+                                       f"{device}: move the module with .to(device) first")
                 t = t.detach().contiguous()
                 keep.append(t)
                 setattr(arr[l], field, t.data_ptr())
@@ -98,22 +116,20 @@ class EncoderEngine:
         return buf
 
     # ---- buffers -------------------------------------------------------------------------------
-    def _workspace(self, B: int, T: int, device: torch.device, tag: str) -> torch.Tensor:
-        key = (device.index or 0, B, T, tag)
+    def _workspace(self, B: int, T: int, device: torch.device, stream: int) -> torch.Tensor:
+        """The direct-launch workspace: ONE buffer per (device, stream), grown to the largest shape seen (its layout
+        is carved per call by the library, so any buffer that is large enough serves every shape)."""
+        key = (device.index or 0, stream)
+        nbytes = max(int(lib.avsr_workspace_bytes(C.byref(self.cfg), B, T)), 256)
         ws = self._workspaces.get(key)
-        if ws is None:
-            nbytes = lib.avsr_workspace_bytes(C.byref(self.cfg), B, T)
-            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes + nbytes // 4, dtype=torch.uint8, device=device)   # 25 % slack: fewer regrowths
             self._workspaces[key] = ws
-            while len(self._workspaces) > 2 * self.MAX_PLANS:
-                self._workspaces.popitem(last=False)
-        else:
-            self._workspaces.move_to_end(key)
         return ws
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, prepared: torch.Tensor, xs: torch.Tensor, lengths: Optional[torch.Tensor], precision: str,
-                use_graph: bool = True, taps: Optional[torch.Tensor] = None) -> torch.Tensor:
+                use_graph: bool = True, taps: Optional[torch.Tensor] = None, check_saturation: bool = False) -> torch.Tensor:
         require_cuda(xs, "xs")
         if xs.dim() != 3 or xs.size(2) != self.cfg.d_model:
             raise ValueError(f"xs must be (B, T, {self.cfg.d_model}), got {tuple(xs.shape)}")
@@ -130,12 +146,28 @@ class EncoderEngine:
         prec = PRECISIONS[precision]
         with torch.cuda.device(device):
             st = _stream_handle(device)
-            if use_graph and taps is None:
-                plan = self._plan(prepared, B, T, device, prec)
+            plan = None
+            if use_graph and taps is None and not check_saturation:
+                plan = self._plan(prepared, B, T, device, prec, st)
+            if plan is not None:
+                self.stats["graph"] += 1
                 check(lib.avsr_plan_forward(plan, xs.data_ptr(), _ptr(lengths), out.data_ptr(), st))
             else:
-                ws = self._workspace(B, T, device, "direct")
-                if taps is None:
+                self.stats["direct"] += 1
+                ws = self._workspace(B, T, device, st)
+                if check_saturation:
+                    cnt = self._sat.get(device.index or 0)
+                    if cnt is None:
+                        cnt = self._sat[device.index or 0] = torch.zeros(1, dtype=torch.int64, device=device)
+                    check(lib.avsr_encoder_forward_checked(C.byref(self.cfg), prepared.data_ptr(), xs.data_ptr(),
+                                                           _ptr(lengths), B, T, out.data_ptr(), ws.data_ptr(),
+                                                           ws.numel(), prec, cnt.data_ptr(), st))
+                    n = int(cnt.item())                      # host sync: this is the diagnostic path
+                    if n:
+                        raise SaturationError(
+                            f"{n} fp16 operand value(s) saturated at +-65504 (or NaN) in this forward: the f16 path "
+                            "is outside its range for these weights / inputs -- use precision='tf32' or 'fp32'")
+                elif taps is None:
                     check(lib.avsr_encoder_forward(C.byref(self.cfg), prepared.data_ptr(), xs.data_ptr(), _ptr(lengths),
                                                    B, T, out.data_ptr(), ws.data_ptr(), ws.numel(), prec, st))
                 else:
@@ -144,12 +176,22 @@ class EncoderEngine:
                                                         ws.data_ptr(), ws.numel(), prec, st))
         return out
 
-    def _plan(self, prepared: torch.Tensor, B: int, T: int, device: torch.device, prec: int):
-        key = (device.index or 0, B, T, prec, prepared.data_ptr())
+    def _plan(self, prepared: torch.Tensor, B: int, T: int, device: torch.device, prec: int, stream: int):
+        """The plan for this shape, or None while the shape has been seen fewer than ``graph_after`` times.  A plan's
+        workspace is private to it and to the stream it was built for (two streams never share one)."""
+        key = (device.index or 0, B, T, prec, prepared.data_ptr(), stream)
         hit = self._plans.get(key)
         if hit is not None:
             self._plans.move_to_end(key)
             return hit[0]
+        seen = self._seen.get(key, 0) + 1
+        self._seen[key] = seen
+        self._seen.move_to_end(key)
+        while len(self._seen) > 64 * self.MAX_PLANS:
+            self._seen.popitem(last=False)
+        if seen < self.graph_after:
+            return None
+        self.stats["plans_built"] += 1
         ws = torch.empty(int(lib.avsr_workspace_bytes(C.byref(self.cfg), B, T)), dtype=torch.uint8, device=device)
         idx = device.index or 0
         if idx not in self._capture_stream:

@@ -9,12 +9,24 @@ from .. import ops
 from ..engine import default_precision
 
 
-def mask_to_lengths(mask: torch.Tensor, B: int, T: int) -> torch.Tensor:
+def mask_to_lengths(mask: torch.Tensor, B: int, T: int, check: bool = False) -> torch.Tensor:
     """(B,1,T) bool key mask from make_non_pad_mask (nets_utils.py:183; True = valid, prefix-contiguous)
-    -> int32 lengths (B) on the same device, without a host sync."""
+    -> int32 lengths (B) on the same device, without a host sync.
+
+    Restriction: the mask must be a PREFIX mask (valid frames first), which is what every caller in
+    the reference passes (e2e_asr_conformer.py:67).  A mask with holes or left padding cannot be expressed as lengths;
+    ``check=True`` (ConformerEncoder.check_mask / AVSR_B200_CHECK_MASK=1) verifies the property at the cost of one
+    host sync and raises instead of computing attention over the wrong keys."""
     if mask.dim() != 3 or mask.size(0) != B or mask.size(1) != 1 or mask.size(2) != T:
         raise NotImplementedError(f"only (B,1,T) key-padding masks are supported, got {tuple(mask.shape)}")
-    return mask[:, 0, :].to(torch.int32).sum(dim=-1, dtype=torch.int32)
+    m = mask[:, 0, :].to(torch.bool)
+    lengths = m.to(torch.int32).sum(dim=-1, dtype=torch.int32)
+    if check:
+        prefix = torch.arange(T, device=mask.device)[None, :] < lengths[:, None]
+        if not bool(torch.equal(prefix, m)):
+            raise NotImplementedError("key mask is not prefix-contiguous (holes / left padding): the B200 path takes "
+                                      "lengths, i.e. make_non_pad_mask-style masks only")
+    return lengths
 
 
 class RelPositionMultiHeadedAttention(nn.Module):

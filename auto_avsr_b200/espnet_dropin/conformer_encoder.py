@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import copy
 import logging
+import os
 from typing import Optional
 
 import torch
@@ -130,8 +131,11 @@ class ConformerEncoder(torch.nn.Module):
 
     ``forward(xs (B,T,d) f32, masks (B,1,T) bool | None) -> (xs (B,T,d), masks)``: one call into the C ABI
     (``avsr_plan_forward``: CUDA-graph replay of the whole 12-layer schedule).  Extra attributes:
-    ``precision`` ("tf32" tensor-core path | "fp32" CUDA-core reference path), ``use_graph``,
-    ``assume_frozen`` (skip the per-call parameter-version check), ``refresh_weights()``.
+    ``precision`` ("f16" default | "tf32" | "fp32" CUDA-core reference path), ``use_graph`` / ``graph_after`` (a
+    shape runs on direct launches until seen ``graph_after`` times, then from its CUDA graph), ``assume_frozen`` (skip
+    the per-call parameter-version check), ``check_saturation`` (diagnostic forward that raises ``SaturationError``
+    when an fp16 operand hit +-65504; env AVSR_B200_CHECK_SAT=1), ``check_mask`` (verify that ``masks`` is a prefix
+    mask; env AVSR_B200_CHECK_MASK=1), ``refresh_weights()``.
     """
 
     def __init__(self, attention_dim=768, attention_heads=12, linear_units=3072, num_blocks=12, dropout_rate=0.1,
@@ -160,7 +164,10 @@ class ConformerEncoder(torch.nn.Module):
         self._cfg = (attention_dim, attention_heads, linear_units, num_blocks, cnn_module_kernel)
         self.precision: Optional[str] = None
         self.use_graph = True
+        self.graph_after: Optional[int] = None      # None: EncoderEngine.GRAPH_AFTER (3); 1: capture at first sight
         self.assume_frozen = False
+        self.check_saturation = os.environ.get("AVSR_B200_CHECK_SAT", "0") == "1"
+        self.check_mask = os.environ.get("AVSR_B200_CHECK_MASK", "0") == "1"
         self._engine: Optional[EncoderEngine] = None
         self._tracked = None
         self._fingerprint = None
@@ -187,6 +194,8 @@ class ConformerEncoder(torch.nn.Module):
     def _prepared(self, device, precision):
         if self._engine is None:
             self._engine = EncoderEngine(*self._cfg)
+        if self.graph_after is not None:
+            self._engine.graph_after = int(self.graph_after)
         if not (self.assume_frozen and self._fingerprint is not None):
             fp = self._weights_fingerprint()
             if fp != self._fingerprint:
@@ -205,8 +214,8 @@ class ConformerEncoder(torch.nn.Module):
                                "move the encoder and its input to a CUDA (B200) device")
         torch.empty(len(self.encoders)).uniform_()     # the reference draws these CPU uniforms every call (repeat.py:23)
         precision = self.precision or default_precision()
-        lengths = None if masks is None else mask_to_lengths(masks, xs.size(0), xs.size(1))
+        lengths = None if masks is None else mask_to_lengths(masks, xs.size(0), xs.size(1), check=self.check_mask)
         prepared = self._prepared(xs.device, precision)
         out = self._engine.forward(prepared, xs.detach().float(), lengths, precision, use_graph=self.use_graph,
-                                   taps=taps)
+                                   taps=taps, check_saturation=self.check_saturation)
         return out, masks

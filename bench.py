@@ -6,9 +6,10 @@
 A step = one ConformerEncoder.forward (embed + 12 layers + after_norm, eval) over one synthetic max-frames=1600
 bucket per GPU (workload S2 = 4 utterances x 400 frames, d=768, BASELINE.json configs[1]); weak scaling: every
 rank gets its own bucket, no collective on the data path; value = all ranks' valid frames / max-over-ranks time.
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference (oracle/) on the
-host cores instead (the reference itself is Python and lives outside the repo, so it cannot travel to the GPU
-box; the oracle is pinned to it by tests/test_oracle_golden.py).
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU implementation on the host cores
+instead: the unmodified espnet modules copied into the git-ignored oracle/_ref by oracle/build_ref.py (kind
+"reference"; the copy travels to the GPU box with the snapshot), or, when that copy is absent, the CPU restatement
+oracle/conformer_oracle.py (kind "port", pinned to the reference by tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 
@@ -31,6 +32,19 @@ from auto_avsr_b200.synthetic import SHAPES, encoder_input, encoder_state_dict  
 WORKLOAD = "S2"
 CFG = dict(d_model=768, n_heads=12, linear_units=3072, num_blocks=12, cnn_kernel=31)
 METRIC = "conformer_encoder_frames_per_sec_max_frames_1600"
+
+
+def workload_string(name=None):
+    """ONE description of the workload for both arms (the driver compares the two `config.workload` strings)."""
+    name = name or WORKLOAD
+    return (f"{name}: lengths={list(SHAPES[name])} (max-frames=1600 per GPU), d=768 H=12 ff=3072 L=12 k=31, eval forward, "
+            "BASELINE.json configs[1]")
+
+
+def non_pad_mask(lengths, device):
+    """make_non_pad_mask(lengths).unsqueeze(-2) (e2e_asr_conformer.py:67) built with torch on the device."""
+    ln = torch.tensor(list(lengths), device=device)
+    return (torch.arange(int(max(lengths)), device=device)[None, :] < ln[:, None]).unsqueeze(1)
 
 
 def algorithmic_flops(lengths, warm_pos_cache=False):
@@ -104,50 +118,78 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+class CpuEncoder:
+    """The reference's own CPU implementation of the path when oracle/_ref was built (kind "reference": the unmodified
+    espnet modules, copied by oracle/build_ref.py), else the CPU restatement oracle/conformer_oracle.py (kind "port").
+    Same synthetic weights and inputs as the GPU arm; eval mode, no_grad, fp32."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.sd = encoder_state_dict(0, **cfg)
+        self.kind = "port"
+        self.enc = None
+        try:
+            from oracle.build_ref import available, import_reference_encoder
+            if available():
+                Ref, _ = import_reference_encoder()
+                enc = Ref(attention_dim=cfg["d_model"], attention_heads=cfg["n_heads"], linear_units=cfg["linear_units"],
+                          num_blocks=cfg["num_blocks"], cnn_module_kernel=cfg["cnn_kernel"])
+                enc.load_state_dict(self.sd, strict=True)
+                self.enc = enc.eval()
+                self.kind = "reference"
+        except Exception as e:      # noqa: BLE001 -- any import problem falls back to the port, loudly
+            log(f"oracle/_ref unusable ({type(e).__name__}: {e}); timing the CPU port instead")
+        if self.enc is None:
+            from oracle import conformer_oracle as O
+            self.O = O
+
+    def forward(self, xs, lengths):
+        with torch.no_grad():
+            if self.enc is not None:
+                mask = non_pad_mask(lengths, "cpu")
+                return self.enc(xs, mask)[0]
+            return self.O.encoder_forward(self.sd, xs, lengths, self.cfg["n_heads"])
+
+
 def pick_threads(lengths):
-    """The oracle is many mid-sized torch ops; on a many-core host all-threads is far from optimal (128 threads were
-    30x slower than 16 on the first B200 box).  Probe a 1-layer forward at a few thread counts and keep the fastest:
-    'all the host threads it can use' productively."""
-    from oracle import conformer_oracle as O
+    """Both CPU implementations are many mid-sized torch ops; on a many-core host all-threads is far from optimal (128
+    threads were 30x slower than 32 on the first B200 box).  Probe a 1-layer forward at a few thread counts and keep
+    the fastest: 'all the host threads it can use' productively."""
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
-    cfg1 = dict(CFG, num_blocks=1)
-    sd = encoder_state_dict(0, **cfg1)
+    cpu1 = CpuEncoder(dict(CFG, num_blocks=1))
     xs = encoder_input(lengths, CFG["d_model"], 1234)
     best, best_t, worse = cands[0], float("inf"), 0
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
-            t0 = time.perf_counter()
-            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
-            dt = time.perf_counter() - t0
-            log(f"cpu probe: {c} threads -> {dt * 1e3:.0f} ms / layer")
-            if dt < best_t:
-                best, best_t, worse = c, dt, 0
-            else:
-                worse += 1
-                if worse >= 2:
-                    break
-    return best
-
-
-def cpu_oracle_time(lengths, repeats, threads):
-    """Best-of-`repeats` wall time of one forward of the CPU oracle (fp32, eval) on `threads` host threads."""
-    from oracle import conformer_oracle as O
-    torch.set_num_threads(threads)
-    sd = encoder_state_dict(0, **CFG)
-    xs = encoder_input(lengths, CFG["d_model"], 1234)
-    with torch.no_grad():
+    for c in cands:
+        torch.set_num_threads(c)
+        cpu1.forward(xs, lengths)
         t0 = time.perf_counter()
-        O.encoder_forward(sd, xs, lengths, CFG["n_heads"])          # warm-up
-        warm = time.perf_counter() - t0
-        best = float("inf")
-        for _ in range(repeats if warm < 8 else 1):                 # bounded: ~10-30 s of CPU work in total
-            t0 = time.perf_counter()
-            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
-            best = min(best, time.perf_counter() - t0)
+        cpu1.forward(xs, lengths)
+        dt = time.perf_counter() - t0
+        log(f"cpu probe ({cpu1.kind}): {c} threads -> {dt * 1e3:.0f} ms / layer")
+        if dt < best_t:
+            best, best_t, worse = c, dt, 0
+        else:
+            worse += 1
+            if worse >= 2:
+                break
     return best
+
+
+def cpu_time(lengths, repeats, threads):
+    """Best-of-`repeats` wall time of one full forward on `threads` host threads -> (seconds, kind)."""
+    torch.set_num_threads(threads)
+    cpu = CpuEncoder(CFG)
+    xs = encoder_input(lengths, CFG["d_model"], 1234)
+    t0 = time.perf_counter()
+    cpu.forward(xs, lengths)                                        # warm-up
+    warm = time.perf_counter() - t0
+    best = float("inf")
+    for _ in range(repeats if warm < 8 else 1):                     # bounded: ~10-30 s of CPU work in total
+        t0 = time.perf_counter()
+        cpu.forward(xs, lengths)
+        best = min(best, time.perf_counter() - t0)
+    return best, cpu.kind
 
 
 def run_reference(args):
@@ -156,29 +198,28 @@ def run_reference(args):
         return
     lengths = list(SHAPES[WORKLOAD])
     threads = pick_threads(lengths)
-    from oracle import conformer_oracle as O
     torch.set_num_threads(threads)
-    sd = encoder_state_dict(0, **CFG)
+    cpu = CpuEncoder(CFG)
     xs = encoder_input(lengths, CFG["d_model"], 1234)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        O.encoder_forward(sd, xs, lengths, CFG["n_heads"])          # warm-up (1 forward; each is a full S2 bucket)
-        warm = time.perf_counter() - t0
-        if warm * args.steps > 120:                                 # keep the arm within a few minutes
-            args.steps = max(1, int(120 / warm))
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.encoder_forward(sd, xs, lengths, CFG["n_heads"])
-        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cpu.forward(xs, lengths)                                        # warm-up (1 forward; each is a full S2 bucket)
+    warm = time.perf_counter() - t0
+    if warm * args.steps > 120:                                     # keep the arm within a few minutes
+        args.steps = max(1, int(120 / warm))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.forward(xs, lengths)
+    dt = time.perf_counter() - t0
     fps = sum(lengths) * args.steps / dt
+    note = ("the reference's own espnet ConformerEncoder (oracle/_ref: unmodified copy made by oracle/build_ref.py)"
+            if cpu.kind == "reference" else
+            "CPU restatement of the reference encoder (oracle/, pinned to reference golden vectors)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD} lengths={lengths} d=768 L=12 (BASELINE.json configs[1])",
-                   "impl_note": "CPU restatement of the reference encoder (oracle/, pinned to reference golden "
-                                "vectors); rank 0 only, host cores"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+        "config": {"workload": workload_string(), "impl_note": note + "; rank 0 only, host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "host_cpus": os.cpu_count(), "kind": cpu.kind,
                          "sample": f"{args.steps} full forwards of workload {WORKLOAD} (1600 frames each)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -248,6 +289,97 @@ def kernel_roofline(dev, peaks, precision):
     return out
 
 
+def time_forward(enc, xs, mask, steps, warm=6):
+    """ms per forward of `enc` on device-resident inputs (CUDA events on the launch stream, after warm-up)."""
+    with torch.no_grad():
+        for _ in range(warm):
+            enc(xs, mask)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            enc(xs, mask)
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def extras(dev, enc, args, peaks):
+    """Numbers that explain / frame the headline (none of them is the headline):
+    shapes      device-resident frames/s of the other SURVEY.md section 8d shapes in the product arithmetic
+    precisions  S2 in tf32 and fp32 modes (the fp32-class accuracy paths) next to f16
+    sustained   S2 replayed back to back for >= 3 s, against MEASURED_PEAKS' sustained bf16 figure
+    gpu_eager_baseline   the same op sequence in stock eager PyTorch on this GPU (cuBLAS / ATen kernels): the torch
+                restatement oracle/conformer_oracle.py moved to cuda, fp32 with and without allow_tf32 -- SURVEY.md
+                section 2b's per-kernel bar ("beat eager PyTorch-on-B200 of the same op sequence")."""
+    out = {"shapes": {}, "precisions": {}}
+    prec0 = enc.precision
+    for name in ("S1", "S2r", "S3", "S4"):
+        lengths = list(SHAPES[name])
+        xs = encoder_input(lengths, CFG["d_model"], 1234).to(dev)
+        mask = None if name == "S1" else non_pad_mask(lengths, dev)
+        ms = time_forward(enc, xs, mask, 20)
+        fl = algorithmic_flops(lengths)
+        out["shapes"][name] = {"lengths": lengths if len(lengths) <= 5 else f"[{lengths[0]}]x{len(lengths)}",
+                               "frames_per_s": sum(lengths) / (ms * 1e-3), "ms_per_step": ms,
+                               "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        log(f"extras: {name} {ms:.3f} ms")
+    lengths = list(SHAPES[WORKLOAD])
+    xs = encoder_input(lengths, CFG["d_model"], 1234).to(dev)
+    mask = non_pad_mask(lengths, dev)
+    for prec, steps in (("tf32", 10), ("fp32", 3)):
+        enc.precision = prec
+        ms = time_forward(enc, xs, mask, steps, warm=3)
+        out["precisions"][prec] = {"frames_per_s": sum(lengths) / (ms * 1e-3), "ms_per_step": ms}
+        log(f"extras: S2 {prec} {ms:.3f} ms")
+    enc.precision = prec0
+    # sustained: >= 3 s of back-to-back replays (clocks settle to the sustained point)
+    ms1 = time_forward(enc, xs, mask, 20)
+    n = max(50, int(3200.0 / ms1))
+    ms = time_forward(enc, xs, mask, n, warm=3)
+    fl = algorithmic_flops(lengths)
+    out["sustained"] = {"seconds": n * ms * 1e-3, "steps": n, "frames_per_s": sum(lengths) / (ms * 1e-3), "ms_per_step": ms,
+                        "frac_of_bf16_sustained_peak": (fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"])
+                        if peaks.get("bf16_tflops_sustained") else None}
+    log(f"extras: sustained {ms:.3f} ms/step over {n * ms * 1e-3:.1f} s")
+    # eager-PyTorch comparator on the same GPU (cuBLAS / ATen), same weights and inputs: the UNMODIFIED reference
+    # modules moved to cuda when oracle/_ref was built, else the torch restatement (oracle/conformer_oracle.py)
+    try:
+        cpu = CpuEncoder(CFG)                          # baseline leg only: the comparator, never the product path
+        if cpu.enc is not None:
+            ref = cpu.enc.to(dev)
+            run = lambda: ref(xs, mask)[0]             # noqa: E731
+            what = "the reference's own espnet ConformerEncoder (oracle/_ref, unmodified) .to('cuda')"
+        else:
+            sd = {k: v.to(dev) for k, v in cpu.sd.items()}
+            run = lambda: cpu.O.encoder_forward(sd, xs, lengths, CFG["n_heads"])   # noqa: E731
+            what = "oracle/conformer_oracle.py (torch restatement of the reference encoder) on cuda"
+        eager = {}
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(3):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            eager["tf32" if tf32 else "fp32"] = {"frames_per_s": sum(lengths) / (ms * 1e-3), "ms_per_step": ms}
+            log(f"extras: eager PyTorch allow_tf32={tf32} {ms:.3f} ms")
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        eager["what"] = what + ": stock eager PyTorch kernels (cuBLAS / cuDNN / ATen), device-resident inputs"
+        out["gpu_eager_baseline"] = eager
+    except Exception as e:          # noqa: BLE001
+        out["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def run_ours(args):
     rank, local_rank, world = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (the encoder path has no CPU fallback)"
@@ -257,7 +389,6 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from auto_avsr_b200 import ConformerEncoder, _cabi
-    from oracle import conformer_oracle as O   # only non_pad_mask + the cpu_baseline leg
 
     lengths = list(SHAPES[WORKLOAD])
     B, T, D = len(lengths), max(lengths), CFG["d_model"]
@@ -267,7 +398,7 @@ def run_ours(args):
     enc = enc.to(dev).eval()
     enc.precision = args.precision
     enc.assume_frozen = True
-    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+    mask = non_pad_mask(lengths, dev)
     nbuf = 4     # rotating inputs; the 682 MB of weights streamed every step already exceed the 126 MB L2
     host_in = [encoder_input(lengths, D, 1234 + rank * 100 + i).pin_memory() for i in range(nbuf)]
     dev_in = [h.to(dev) for h in host_in]
@@ -344,12 +475,12 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"f16": "f16 operands, f32 accumulate (f32 residual/LN/softmax)", "tf32": "tf32 operands, f32 accumulate",
                       "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: lengths={lengths} (max-frames=1600 per GPU), d=768 H=12 ff=3072 L=12 k=31, "
-                                   "eval forward, BASELINE.json configs[1]",
+            "config": {"workload": workload_string(),
                        "global_frames_per_step": sum(lengths) * world, "parallelism": f"dp{world} (one bucket per GPU, "
                                                                                        "no data-path collective)",
                        "l2": "682 MB of weights streamed per step > 126 MB L2; 4 rotating input buffers",
                        "pos_cache": "cold: linear_pos(pos_emb) recomputed every step", "precision": args.precision,
+                       "assume_frozen": True, "graph_after": enc._engine.graph_after,
                        "untimed_steps_before_timing": n_warm},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 4 + B * 4,
                     "d2h_bytes_per_step": B * T * D * 4, "ms_per_step": e2e_ms_max / args.steps,
@@ -364,12 +495,14 @@ def run_ours(args):
         if args.precision != "fp32":
             line["roofline"] = kernel_roofline(dev, peaks, args.precision)
             log("kernel roofline done")
+        if world == 1 and not args.no_extras:
+            line["extras"] = extras(dev, enc, args, peaks)
         if world == 1 and not args.no_cpu:
             threads = pick_threads(lengths)
-            best = cpu_oracle_time(lengths, repeats=3, threads=threads)
-            log(f"cpu baseline done: {best:.3f} s/forward on {threads} threads")
+            best, kind = cpu_time(lengths, repeats=3, threads=threads)
+            log(f"cpu baseline ({kind}) done: {best:.3f} s/forward on {threads} threads")
             line["cpu_baseline"] = {"value": sum(lengths) / best, "unit": "frames/s", "cores": threads, "host_cpus": os.cpu_count(),
-                                    "kind": "port", "sample": f"best of 3 full forwards of workload {WORKLOAD} (1600 frames), fp32, "
+                                    "kind": kind, "sample": f"best of 3 full forwards of workload {WORKLOAD} (1600 frames), fp32, "
                                               "after 1 warm-up"}
         print(json.dumps(line))
     if world > 1:
@@ -386,6 +519,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("AVSR_B200_PRECISION", "f16"),
                     choices=["f16", "tf32", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extras (other shapes / precisions, sustained "
+                                                               "loop, eager-PyTorch GPU comparator)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:

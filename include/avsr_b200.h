@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 2
+#define AVSR_ABI_VERSION 3
 
 enum {
   AVSR_OK = 0,
@@ -104,6 +104,15 @@ size_t avsr_workspace_bytes(const AvsrEncoderConfig *cfg, int B, int T);
 int avsr_encoder_forward(const AvsrEncoderConfig *cfg, const void *prepared, const float *xs,
                          const int32_t *lengths, int B, int T, float *out, void *workspace,
                          size_t workspace_bytes, int precision, void *stream);
+
+/* Diagnostic variant of avsr_encoder_forward for AVSR_PREC_F16: fp16 operand stores saturate at +-65504
+ * (cvt.rn.satfinite) where the fp32 reference would carry on.  This entry scans every operand tensor (LayerNorm
+ * outputs, FFN hidden, q/k/v, rel-pos table, attention context, conv activations) right after its producer and
+ * leaves in *saturated (DEVICE uint64, zeroed by the call) the number of elements that sit at the saturation value or
+ * are NaN.  0 == the fp16 path stayed in range for these weights and inputs.  Direct launches, ~2x slower. */
+int avsr_encoder_forward_checked(const AvsrEncoderConfig *cfg, const void *prepared, const float *xs,
+                                 const int32_t *lengths, int B, int T, float *out, void *workspace,
+                                 size_t workspace_bytes, int precision, uint64_t *saturated, void *stream);
 
 /* Same computation replayed from a CUDA graph captured once per (B, T, buffers): removes the ~190
  * per-forward launches' host cost.  The plan is HOST state only (tensor maps + graph); it borrows

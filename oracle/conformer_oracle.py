@@ -77,8 +77,8 @@ def rel_attention_scores(q: Tensor, k: Tensor, p: Tensor, u: Tensor, v: Tensor) 
     B, H, T, dk = q.shape
     ac = torch.einsum("bhid,bhjd->bhij", q + u[None, :, None, :], k)
     bd_raw = torch.einsum("bhid,hmd->bhim", q + v[None, :, None, :], p)       # (B,H,T,2T-1)
-    i = torch.arange(T).unsqueeze(1)
-    j = torch.arange(T).unsqueeze(0)
+    i = torch.arange(T, device=q.device).unsqueeze(1)
+    j = torch.arange(T, device=q.device).unsqueeze(0)
     m = (j - i + T - 1).expand(B, H, T, T)
     bd = torch.gather(bd_raw, 3, m)
     return (ac + bd) / math.sqrt(dk)
@@ -104,7 +104,7 @@ def rel_mha(x: Tensor, pos_emb: Tensor, lengths: Optional[Tensor], sd: Dict[str,
     p = (pos_emb @ sd[pfx + "linear_pos.weight"].T).view(2 * T - 1, n_heads, dk).transpose(0, 1)
     scores = rel_attention_scores(q, k, p, sd[pfx + "pos_bias_u"], sd[pfx + "pos_bias_v"])
     if lengths is not None:
-        key_pad = torch.arange(T)[None, :] >= lengths.view(B, 1)               # (B,T) True = padded
+        key_pad = torch.arange(T, device=x.device)[None, :] >= lengths.view(B, 1)   # (B,T) True = padded
         scores = scores.masked_fill(key_pad[:, None, None, :], float("-inf"))
         smax = scores.amax(dim=-1, keepdim=True)
         smax = torch.where(torch.isinf(smax), torch.zeros_like(smax), smax)
@@ -185,8 +185,8 @@ def encoder_forward(sd: Dict[str, Tensor], xs: Tensor, lengths: Optional[Sequenc
     sd = {k: (t.to(dtype) if t.is_floating_point() else t) for k, t in sd.items()}
     B, T, D = xs.shape
     x = xs * math.sqrt(D)                                                       # embedding.py:178
-    pos_emb = rel_sinusoid_table(T, D, dtype)                                   # embedding.py:179-183
-    len_t = None if lengths is None else torch.as_tensor(list(lengths), dtype=torch.long)
+    pos_emb = rel_sinusoid_table(T, D, dtype).to(xs.device)                     # embedding.py:179-183
+    len_t = None if lengths is None else torch.as_tensor(list(lengths), dtype=torch.long, device=xs.device)
     for l in range(count_layers(sd)):
         x = encoder_layer(x, pos_emb, len_t, sd, f"encoders.{l}.", n_heads,
                           stages if l == 0 else None)

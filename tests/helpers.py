@@ -36,3 +36,20 @@ def load_head_case(name):
 def err_stats(a, b):
     d = (a.double() - b.double()).abs()
     return d.max().item(), d.pow(2).mean().sqrt().item()
+
+
+_OBS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def record(test, case, observed, bound):
+    """Print the observed error next to its bound and append it to gpurun_out/parity_observed.jsonl (the GPU runs'
+    scratch directory) so that the bounds in the tests can be kept at <= 4x what a B200 actually produces."""
+    import json
+    line = {"test": test, "case": str(case), "observed": observed, "bound": bound}
+    print("PARITY", json.dumps(line))
+    try:
+        os.makedirs(_OBS, exist_ok=True)
+        with open(os.path.join(_OBS, "parity_observed.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+    except OSError:
+        pass

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(syms) <= exported, sorted(set(syms) - exported)
     from auto_avsr_b200 import _cabi
     assert set(_cabi.SIGNATURES) == set(syms)
-    assert _cabi.lib.avsr_abi_version() == _cabi.ABI_VERSION == 2
+    assert _cabi.lib.avsr_abi_version() == _cabi.ABI_VERSION == 3
     assert _cabi.launch_count() == 0
 
 
@@ -209,3 +209,15 @@ print("OK")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+def test_mask_to_lengths_prefix_check():
+    """a key mask that is not prefix-contiguous cannot be expressed as lengths; check=True raises."""
+    import torch
+    from auto_avsr_b200.espnet_dropin.attention import mask_to_lengths
+    ok = torch.tensor([[[1, 1, 1, 0, 0]], [[1, 1, 1, 1, 1]]], dtype=torch.bool)
+    assert mask_to_lengths(ok, 2, 5, check=True).tolist() == [3, 5]
+    bad = torch.tensor([[[1, 0, 1, 0, 0]], [[1, 1, 1, 1, 1]]], dtype=torch.bool)
+    assert mask_to_lengths(bad, 2, 5).tolist() == [2, 5]            # unchecked: silently a prefix of 2 (documented)
+    with pytest.raises(NotImplementedError):
+        mask_to_lengths(bad, 2, 5, check=True)

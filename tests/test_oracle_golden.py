@@ -106,3 +106,26 @@ def test_zero_length_row_is_zero_attention():
                     "encoders.0.self_attn.", 2)
     bias = sd["encoders.0.self_attn.linear_out.bias"]
     assert torch.allclose(out[1], bias.expand(T, D), atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["tiny_ragged", "tiny_k7_nomask", "full2_ragged"])
+def test_ref_copy_reproduces_golden(name):
+    """oracle/_ref (verbatim copy of the reference encoder modules made by oracle/build_ref.py; what bench.py's
+    reference arm and cpu_baseline leg time) reproduces the committed fixtures, i.e. it IS the code that generated them."""
+    from oracle import build_ref
+    build_ref.build()
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built (no /root/reference in this environment)")
+    Ref, make_non_pad_mask = build_ref.import_reference_encoder()
+    c = load_case(name)
+    cfg = c["cfg"]
+    enc = Ref(attention_dim=cfg["d_model"], attention_heads=cfg["n_heads"], linear_units=cfg["linear_units"],
+              num_blocks=cfg["num_blocks"], cnn_module_kernel=cfg["cnn_kernel"])
+    enc.load_state_dict(c["sd"], strict=True)
+    enc = enc.double().eval()
+    mask = make_non_pad_mask(c["lengths"]).unsqueeze(-2) if c["masked"] else None
+    with torch.no_grad():
+        out = enc(c["xs"].double(), mask)[0]
+    mx, _ = err_stats(out, torch.from_numpy(c["z"]["out_f64"]))
+    # the full-size fixtures keep the fp64 output rounded to fp32 (oracle/make_golden.py): <= 6e-8 relative
+    assert mx < (1e-12 if cfg["d_model"] <= 128 else 5e-7), mx
