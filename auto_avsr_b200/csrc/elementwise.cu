@@ -34,221 +34,222 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 }
 
 // ------------------------------------------------------------------ LayerNorm (layer_norm.py:21, eps 1e-12)
-// One warp per row; the row lives in registers (d <= 1024) so HBM sees exactly one read and one write.
-// Two-pass mean / centred variance, warp-shuffle reductions.
-constexpr int kLnMaxVec = 8;  // 8 float4 per lane * 32 lanes = 1024 channels
+// A row (d <= 1024 channels) is held in registers by WPR warps (1, 2 or 4): HBM / L2 sees exactly one read and one
+// write per element.  Two-pass mean / centred variance; warp-shuffle reductions, combined across the row's warps
+// through shared memory in a fixed order (deterministic).  The r02 launch timeline showed these kernels to be bound by
+// the latency of one load -> reduce -> store chain per warp (1 600 warps on 148 SMs is a single, half-empty wave), so
+// the geometry is a launch parameter: more warps per row = shorter chains and more loads in flight per SM.
+//   TWO = false : y = LN(x; g1, b1)                                   (y in operand storage or fp32)
+//   TWO = true  : y1 = LN(x; g1, b1) (fp32, may alias x) and y = LN(y1; g2, b2) in operand storage -- layer l's
+//                 norm_final followed by layer l+1's norm_ff_macaron (conformer_encoder.py:161-162 then :113).
+//   NP > 0      : deferred split-K residual update applied while the row is loaded (LnParts): row = x + alpha *
+//                 (bias + part[0] + ... + part[NP-1]), fixed order; the updated row is written to pp.x_out when that
+//                 is not already the kernel's own fp32 output.  All loads of the row are issued before the first use
+//                 and before any store (a store in between would serialise them: possible aliasing).
+constexpr int kLnMaxVec = 8;  // float4 per lane at WPR = 1: 8 * 32 lanes * 4 = 1024 channels
 
-// Deferred split-K residual update applied to the row held in v (see LnParts); NP = number of k-slices, a
-// compile-time constant so that every load of the row is issued before the first use.  The caller stores the updated
-// row (pp.x_out) only after ALL its loads: a store in between would serialise them (possible aliasing).
-template <int NP>
-__device__ __forceinline__ void ln_apply_parts(float4 (&v)[8], int lane, int nvec, long row_vec, const LnParts& pp) {
+__device__ __forceinline__ void ln_named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// sum over the row's WPR warps; `slot` = this reduction's private shared-memory cells (never reused in the kernel)
+template <int WPR>
+__device__ __forceinline__ float ln_row_sum(float v, float* slot, int wr, int lane, int bar_id) {
+  v = warp_sum(v);
+  if constexpr (WPR == 1) return v;
+  if (lane == 0) slot[wr] = v;
+  ln_named_bar(bar_id, 32 * WPR);
+  float t = slot[0];
+#pragma unroll
+  for (int w = 1; w < WPR; ++w) t += slot[w];
+  return t;
+}
+
+template <int NP, bool TWO, int WPR, int RPC, int V>   // V = float4 per lane: WPR * 32 * V * 4 >= d
+__global__ void __launch_bounds__(32 * WPR * RPC)
+ln_kernel(const float* x /* may alias y1 / pp.x_out */, const float* __restrict__ g1, const float* __restrict__ b1,
+          const float* __restrict__ g2, const float* __restrict__ b2, float* y1, void* y, int rows, int d,
+          int out_kind, LnParts pp) {
+  constexpr int STEP = 32 * WPR;                // float4 stride between a lane's vectors
+  __shared__ float red[4][RPC][WPR];
+  pdl_launch_dependents();
+  AVSR_TSPAN_OPEN(TWO ? 110 : 100, NP | (WPR << 8) | (RPC << 12));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rl = warp / WPR, wr = warp - rl * WPR;      // row inside the CTA, warp inside the row
+  const int row = blockIdx.x * RPC + rl;
+  if (row >= rows) return;                              // whole rows leave together (named barriers are per row)
+  const int nvec = d >> 2;
+  const int c0 = wr * 32 + lane;
+  // parameters are not produced by the previous kernel: fetch them before waiting on it
+  float4 gg[V], bb[V], gg2[TWO ? V : 1], bb2[TWO ? V : 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = c0 + i * STEP;
+    if (c < nvec) {
+      gg[i] = reinterpret_cast<const float4*>(g1)[c]; bb[i] = reinterpret_cast<const float4*>(b1)[c];
+      if constexpr (TWO) { gg2[i] = reinterpret_cast<const float4*>(g2)[c]; bb2[i] = reinterpret_cast<const float4*>(b2)[c]; }
+    }
+  }
+  float4 pb[NP > 0 ? V : 1];
   if constexpr (NP > 0) {
-    const float4* b4 = reinterpret_cast<const float4*>(pp.bias);
-    const float4* p4 = reinterpret_cast<const float4*>(pp.part) + row_vec;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i * STEP;
+      if (c < nvec) pb[i] = reinterpret_cast<const float4*>(pp.bias)[c];
+    }
+  }
+  pdl_wait();
+  AVSR_TSPAN_DEP();
+  const long rv = (long)row * nvec;
+  const float4* xr = reinterpret_cast<const float4*>(x) + rv;
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = c0 + i * STEP;
+    if (c < nvec) v[i] = xr[c];
+  }
+  if constexpr (NP > 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(pp.part) + rv;
     const long sv = pp.stride >> 2;
+    float4 t[NP][V];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = i * 32 + lane;
+    for (int s = 0; s < NP; ++s)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = c0 + i * STEP;
+        if (c < nvec) t[s][i] = p4[s * sv + c];
+      }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 a = pb[i];
+#pragma unroll
+      for (int s = 0; s < NP; ++s) { a.x += t[s][i].x; a.y += t[s][i].y; a.z += t[s][i].z; a.w += t[s][i].w; }
+      v[i].x += pp.alpha * a.x; v[i].y += pp.alpha * a.y; v[i].z += pp.alpha * a.z; v[i].w += pp.alpha * a.w;
+    }
+  }
+  const int bar_id = 1 + rl;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    if (c0 + i * STEP < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  float mean = ln_row_sum<WPR>(s, red[0][rl], wr, lane, bar_id) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    if (c0 + i * STEP < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  float rstd = 1.0f / sqrtf(ln_row_sum<WPR>(q, red[1][rl], wr, lane, bar_id) / (float)d + 1e-12f);
+  if constexpr (!TWO) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i * STEP;
       if (c < nvec) {
-        float4 a = b4[c];
-#pragma unroll
-        for (int s = 0; s < NP; ++s) {
-          const float4 t = p4[s * sv + c];
-          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-        }
-        v[i].x += pp.alpha * a.x; v[i].y += pp.alpha * a.y; v[i].z += pp.alpha * a.z; v[i].w += pp.alpha * a.w;
+        if (NP > 0 && pp.x_out) reinterpret_cast<float4*>(pp.x_out)[rv + c] = v[i];
+        store_kind4(y, (long)row * d + 4 * c, out_kind, (v[i].x - mean) * rstd * gg[i].x + bb[i].x,
+                    (v[i].y - mean) * rstd * gg[i].y + bb[i].y, (v[i].z - mean) * rstd * gg[i].z + bb[i].z,
+                    (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
       }
     }
-  }
-}
-
-template <int NP>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* x /* may alias y */, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, void* y,
-                                                        int rows, int d, int out_kind, LnParts pp) {
-  pdl_launch_dependents();
-  AVSR_TSPAN_OPEN(100, NP);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
-  const int nvec = d >> 2;
-  // gamma / beta are parameters (not produced by the previous kernel): fetch them before waiting on it
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  float4 gg[kLnMaxVec], bb[kLnMaxVec];
+  } else {
+    float4* y1r = reinterpret_cast<float4*>(y1) + rv;
+    s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) { gg[i] = g4[c]; bb[i] = b4[c]; }
-  }
-  pdl_wait();
-  AVSR_TSPAN_DEP();
-  float4 v[kLnMaxVec];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) v[i] = xr[c];
-  }
-  ln_apply_parts<NP>(v, lane, nvec, (long)warp * nvec, pp);
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(s) / (float)d;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-      q += (a * a + b * b) + (e * e + f * f);
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i * STEP;
+      if (c < nvec) {
+        v[i].x = (v[i].x - mean) * rstd * gg[i].x + bb[i].x;
+        v[i].y = (v[i].y - mean) * rstd * gg[i].y + bb[i].y;
+        v[i].z = (v[i].z - mean) * rstd * gg[i].z + bb[i].z;
+        v[i].w = (v[i].w - mean) * rstd * gg[i].w + bb[i].w;
+        y1r[c] = v[i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
     }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
+    mean = ln_row_sum<WPR>(s, red[2][rl], wr, lane, bar_id) / (float)d;
+    q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) {
-      const float4 g = gg[i], b = bb[i];
-      if (NP > 0 && pp.x_out) reinterpret_cast<float4*>(pp.x_out)[(long)warp * nvec + c] = v[i];
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + b.x;
-      o.y = (v[i].y - mean) * rstd * g.y + b.y;
-      o.z = (v[i].z - mean) * rstd * g.z + b.z;
-      o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      store_kind4(y, (long)warp * d + 4 * c, out_kind, o.x, o.y, o.z, o.w);
+    for (int i = 0; i < V; ++i)
+      if (c0 + i * STEP < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+        q += (a * a + b * b) + (e * e + f * f);
+      }
+    rstd = 1.0f / sqrtf(ln_row_sum<WPR>(q, red[3][rl], wr, lane, bar_id) / (float)d + 1e-12f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i * STEP;
+      if (c < nvec)
+        store_kind4(y, (long)row * d + 4 * c, out_kind, (v[i].x - mean) * rstd * gg2[i].x + bb2[i].x,
+                    (v[i].y - mean) * rstd * gg2[i].y + bb2[i].y, (v[i].z - mean) * rstd * gg2[i].z + bb2[i].z,
+                    (v[i].w - mean) * rstd * gg2[i].w + bb2[i].w);
     }
   }
   AVSR_TSPAN_CLOSE();
 }
 
-// Two chained LayerNorms in one pass over the row: y1 = LN(x; g1, b1) (fp32, may alias x) and
-// y2 = LN(y1; g2, b2) in operand storage -- layer l's norm_final followed by layer l+1's norm_ff_macaron
-// (conformer_encoder.py:161-162 then :113): one read of x instead of two, one launch instead of two.
-template <int NP>
-__global__ void __launch_bounds__(256) layernorm2_kernel(const float* x /* may alias y1 */, const float* __restrict__ g1,
-                                                         const float* __restrict__ b1, const float* __restrict__ g2,
-                                                         const float* __restrict__ b2, float* y1,
-                                                         void* __restrict__ y2, int rows, int d, int out_kind,
-                                                         LnParts pp) {
-  pdl_launch_dependents();
-  AVSR_TSPAN_OPEN(110, NP);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const int nvec = d >> 2;
-  const float4* g14 = reinterpret_cast<const float4*>(g1);
-  const float4* b14 = reinterpret_cast<const float4*>(b1);
-  float4 gg[kLnMaxVec], bb[kLnMaxVec];
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) { gg[i] = g14[c]; bb[i] = b14[c]; }
+// launch geometry: warps per row x rows per CTA.  AVSR_B200_LN="<wpr>x<rows>" overrides (1x8 = the round-1 kernel).
+struct LnGeom { int wpr, rpc; };
+static LnGeom ln_geom(int d) {
+  static const LnGeom env = [] {
+    LnGeom g{0, 0};
+    if (const char* e = getenv("AVSR_B200_LN")) { if (sscanf(e, "%dx%d", &g.wpr, &g.rpc) != 2) g = LnGeom{0, 0}; }
+    return g;
+  }();
+  LnGeom g = env.wpr ? env : LnGeom{2, 2};
+  (void)d;
+  return g;
+}
+
+template <int NP, bool TWO>
+static int launch_ln_np(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
+                        void* y, int rows, int d, int out_kind, cudaStream_t st, const LnParts& pp) {
+  const LnGeom g = ln_geom(d);
+  // vectors per lane: the reference's d = 768 needs 6 / 3 / 2 at 1 / 2 / 4 warps per row; up to 1024 channels 8 / 4 / 2
+  const bool small = d <= 768;
+#define AVSR_LN_CASE(W, R, VS, VL)                                                                                  \
+  if (g.wpr == W && g.rpc == R) {                                                                                   \
+    if (small)                                                                                                      \
+      AVSR_LAUNCH((ln_kernel<NP, TWO, W, R, VS>), cdiv(rows, R), 32 * W * R, 0, st, x, g1, b1, g2, b2, y1, y, rows, \
+                  d, out_kind, pp);                                                                                 \
+    else                                                                                                            \
+      AVSR_LAUNCH((ln_kernel<NP, TWO, W, R, VL>), cdiv(rows, R), 32 * W * R, 0, st, x, g1, b1, g2, b2, y1, y, rows, \
+                  d, out_kind, pp);                                                                                 \
+    return AVSR_OK;                                                                                                 \
   }
-  pdl_wait();
-  AVSR_TSPAN_DEP();
-  const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
-  float4 v[kLnMaxVec];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) v[i] = xr[c];
+  AVSR_LN_CASE(1, 8, 6, 8) AVSR_LN_CASE(1, 2, 6, 8)
+  AVSR_LN_CASE(2, 4, 3, 4) AVSR_LN_CASE(2, 2, 3, 4)
+  AVSR_LN_CASE(4, 2, 2, 2) AVSR_LN_CASE(4, 1, 2, 2)
+#undef AVSR_LN_CASE
+  AVSR_REQUIRE(false, "layernorm: geometry %dx%d not instantiated", g.wpr, g.rpc);
+  return AVSR_OK;
+}
+
+template <bool TWO>
+static int launch_ln(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
+                     void* y, int rows, int d, int out_kind, cudaStream_t st, const LnParts* parts) {
+  AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
+               kLnMaxVec * 128);
+  if (rows <= 0) return AVSR_OK;
+  const LnParts pp = parts ? *parts : LnParts{};
+  switch (pp.nparts) {
+    case 0: return launch_ln_np<0, TWO>(x, g1, b1, g2, b2, y1, y, rows, d, out_kind, st, pp);
+    case 2: return launch_ln_np<2, TWO>(x, g1, b1, g2, b2, y1, y, rows, d, out_kind, st, pp);
+    case 3: return launch_ln_np<3, TWO>(x, g1, b1, g2, b2, y1, y, rows, d, out_kind, st, pp);
+    case 4: return launch_ln_np<4, TWO>(x, g1, b1, g2, b2, y1, y, rows, d, out_kind, st, pp);
+    default: AVSR_REQUIRE(false, "layernorm: %d k-slices not instantiated (0, 2, 3, 4)", pp.nparts);
   }
-  ln_apply_parts<NP>(v, lane, nvec, (long)warp * nvec, pp);
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  float mean = warp_sum(s) / (float)d;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-      q += (a * a + b * b) + (e * e + f * f);
-    }
-  }
-  float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
-  float4* y1r = reinterpret_cast<float4*>(y1 + (long)warp * d);
-  s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) {
-      v[i].x = (v[i].x - mean) * rstd * gg[i].x + bb[i].x;
-      v[i].y = (v[i].y - mean) * rstd * gg[i].y + bb[i].y;
-      v[i].z = (v[i].z - mean) * rstd * gg[i].z + bb[i].z;
-      v[i].w = (v[i].w - mean) * rstd * gg[i].w + bb[i].w;
-      y1r[c] = v[i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-  const float4* g24 = reinterpret_cast<const float4*>(g2);
-  const float4* b24 = reinterpret_cast<const float4*>(b2);
-  mean = warp_sum(s) / (float)d;
-  q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec) {
-      gg[i] = g24[c]; bb[i] = b24[c];
-      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-      q += (a * a + b * b) + (e * e + f * f);
-    }
-  }
-  rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-12f);
-#pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nvec)
-      store_kind4(y2, (long)warp * d + 4 * c, out_kind, (v[i].x - mean) * rstd * gg[i].x + bb[i].x,
-                  (v[i].y - mean) * rstd * gg[i].y + bb[i].y, (v[i].z - mean) * rstd * gg[i].z + bb[i].z,
-                  (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
-  }
-  AVSR_TSPAN_CLOSE();
+  return AVSR_OK;
 }
 
 int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
                       void* y2, int rows, int d, int out_kind, cudaStream_t st, const LnParts* parts) {
-  AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm2: d=%d must be a multiple of 4 and <= %d", d,
-               kLnMaxVec * 128);
-  if (rows <= 0) return AVSR_OK;
-  const int warps_per_block = 8;
-  const LnParts pp = parts ? *parts : LnParts{};
-  const int grid = cdiv(rows, warps_per_block), block = warps_per_block * 32;
-  switch (pp.nparts) {
-    case 0: AVSR_LAUNCH(layernorm2_kernel<0>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
-    case 2: AVSR_LAUNCH(layernorm2_kernel<2>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
-    case 3: AVSR_LAUNCH(layernorm2_kernel<3>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
-    case 4: AVSR_LAUNCH(layernorm2_kernel<4>, grid, block, 0, st, x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, pp); break;
-    default: AVSR_REQUIRE(false, "layernorm2: %d k-slices not instantiated (0, 2, 3, 4)", pp.nparts);
-  }
-  return AVSR_OK;
+  return launch_ln<true>(x, g1, b1, g2, b2, y1, y2, rows, d, out_kind, st, parts);
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st, const LnParts* parts) {
-  AVSR_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128 && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
-               kLnMaxVec * 128);
-  if (rows <= 0) return AVSR_OK;
-  const int warps_per_block = 8;
-  const LnParts pp = parts ? *parts : LnParts{};
-  const int grid = cdiv(rows, warps_per_block), block = warps_per_block * 32;
-  switch (pp.nparts) {
-    case 0: AVSR_LAUNCH(layernorm_kernel<0>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
-    case 2: AVSR_LAUNCH(layernorm_kernel<2>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
-    case 3: AVSR_LAUNCH(layernorm_kernel<3>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
-    case 4: AVSR_LAUNCH(layernorm_kernel<4>, grid, block, 0, st, x, g, b, y, rows, d, out_kind, pp); break;
-    default: AVSR_REQUIRE(false, "layernorm: %d k-slices not instantiated (0, 2, 3, 4)", pp.nparts);
-  }
-  return AVSR_OK;
+  return launch_ln<false>(x, g, b, nullptr, nullptr, nullptr, y, rows, d, out_kind, st, parts);
 }
 
 // ------------------------------------------------------------------ rel-pos sinusoid table (embedding.py:139-184)

@@ -53,7 +53,8 @@ def kind_name(kid, aux):
 def main() -> None:
     workload = sys.argv[1] if len(sys.argv) > 1 else "S2"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    out_path = sys.argv[3] if len(sys.argv) > 3 else None
+    out_path = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "-" else None
+    brief = len(sys.argv) > 4 and sys.argv[4] == "brief"      # per-kind summary only
     dev = torch.device("cuda:0")
     lengths = list(SHAPES[workload])
     enc = ConformerEncoder()
@@ -161,6 +162,10 @@ def main() -> None:
                       f"  ({both.sum()} CTAs)")
             if ok.any():
                 prev = s
+    if brief:
+        a = next(i for i, l in enumerate(lines) if l.startswith("per kernel kind"))
+        b = next(i for i, l in enumerate(lines) if "sum of exposed" in l)
+        lines = lines[:1] + lines[a:b + 1]
     text = "\n".join(lines)
     print(text)
     if out_path:

@@ -1,14 +1,16 @@
 """GPU parity tests proper: every call goes through the C ABI (ctypes) of libavsr_b200.so and is compared with
 the CPU oracle / the committed golden vectors of the reference.
 
-Tolerances (max-abs on outputs of rms ~1 unless noted):
-  fp32 path  (CUDA-core FMA):       2e-4 whole encoder, 2e-5 single ops -- fp32 summation-order noise only
-  tf32 path  (tcgen05 kind::tf32):  2e-2 max-abs / 3e-3 rms whole 12-layer encoder; operands rounded to TF32
-                                    (10-bit mantissa, RN), fp32 accumulate -- the same class of arithmetic
-                                    PyTorch's own `allow_tf32` GPU path uses for the reference.
-  f16 path   (tcgen05 kind::f16):   same bounds: IEEE half operands carry the same 10-bit mantissa as TF32 (values
-                                    saturate at +-65504), fp32 accumulate; residual stream / LN / softmax stay fp32.
-Measured on B200 (full 12-layer golden cases): fp32 ~2e-6, tf32 ~7e-4 max-abs.
+Tolerances are pinned at <= 4x the errors a B200 produced in round 2 (every comparison prints its observed value and
+appends it to gpurun_out/parity_observed.jsonl; the run the bounds come from is profiles/r02_parity_observed.txt).
+Outputs have rms ~1; errors are max-abs / rms against the fp64 reference:
+  fp32 path  (CUDA-core FMA):       observed 8.6e-6 / 6.3e-7 on the 12-layer encoder -- fp32 summation-order noise only
+  tf32 path  (tcgen05 kind::tf32):  observed 4.7e-3 / 3.1e-4 (12 layers), 6.4e-4 / 8.9e-5 (2 layers); operands rounded
+                                    to TF32 (10-bit mantissa, RN), fp32 accumulate -- the arithmetic class of PyTorch's
+                                    own `allow_tf32` GPU path.
+  f16 path   (tcgen05 kind::f16):   observed 4.5e-3 / 3.1e-4 (12 layers), 5.8e-4 / 8.9e-5 (2 layers): IEEE half operands
+                                    carry the same 10-bit mantissa (values saturate at +-65504, see the range tests),
+                                    fp32 accumulate; residual stream / LN / softmax stay fp32.
 """
 import math
 
@@ -22,11 +24,18 @@ from oracle import conformer_oracle as O
 pytestmark = pytest.mark.gpu
 
 PRECS = ["fp32", "tf32", "f16"]
-TOL_ENC = {"fp32": (2e-4, 2e-5), "tf32": (2e-2, 3e-3), "f16": (2e-2, 3e-3)}    # (max-abs, rms) vs the fp64 reference
-TOL_OP = {"fp32": 2e-5, "tf32": 4e-3, "f16": 4e-3}                             # relative to output scale
-TOL_ATT = {"fp32": 2e-5, "tf32": 2e-2, "f16": 2e-2}                            # attention context, relative
-TOL_TAP = {"fp32": 2e-5, "tf32": 3e-3, "f16": 3e-3}                            # layer-0 residual stages, relative
-TOL_BATCH = {"fp32": 1e-5, "tf32": 5e-3, "f16": 5e-3}                          # same utterance in another batch slot
+# (max-abs, rms) vs the fp64 reference on the 12-layer encoder / on encoders of <= 2 layers
+TOL_ENC = {"fp32": (3.5e-5, 2.5e-6), "tf32": (1.8e-2, 1.2e-3), "f16": (1.8e-2, 1.2e-3)}
+TOL_ENC_SHALLOW = {"fp32": (8e-6, 8e-7), "tf32": (2.5e-3, 3.5e-4), "f16": (2.5e-3, 3.5e-4)}
+TOL_OP = {"fp32": 8e-6, "tf32": 4e-3, "f16": 1.5e-3}                           # single GEMMs, relative to output scale
+TOL_ATT = {"fp32": 4e-6, "tf32": 4e-3, "f16": 4e-3}                            # attention context, relative
+TOL_TAP = {"fp32": 1e-6, "tf32": 3.5e-5, "f16": 3.5e-5}                        # layer-0 residual stages, relative
+TOL_BATCH = {"fp32": 1e-5, "tf32": 2e-3, "f16": 2e-3}                          # same utterance in another batch slot
+TOL_EDGE = {"fp32": 1e-5, "tf32": 1.5e-4, "f16": 1.5e-4}                       # 1-layer edge shapes, max-abs
+
+
+def tol_enc(prec, num_blocks):
+    return TOL_ENC[prec] if num_blocks > 2 else TOL_ENC_SHALLOW[prec]
 
 
 @pytest.fixture(scope="module")
@@ -176,8 +185,9 @@ def test_encoder_matches_reference_golden(dev, name, prec):
         out, m = enc(c["xs"].to(dev), _mask(c, dev))
         outs[graph] = out.cpu()
         mx, rms = err_stats(outs[graph], ref)
-        record("encoder_golden", (name, prec, graph), [mx, rms], list(TOL_ENC[prec]))
-        assert mx < TOL_ENC[prec][0] and rms < TOL_ENC[prec][1], (name, prec, graph, mx, rms)
+        tol = tol_enc(prec, c["cfg"]["num_blocks"])
+        record("encoder_golden", (name, prec, graph), [mx, rms], list(tol))
+        assert mx < tol[0] and rms < tol[1], (name, prec, graph, mx, rms)
         assert (m is None) == (not c["masked"])
     assert torch.equal(outs[False], outs[True]), "CUDA-graph replay must be bit-identical to direct launches"
 
@@ -213,8 +223,9 @@ def test_per_module_layer_forward(dev, prec):
     y = enc.after_norm(x).cpu()
     ref = torch.from_numpy(c["z"]["out_f64"])
     mx, rms = err_stats(y, ref)
-    record("per_module", (prec,), [mx, rms], list(TOL_ENC[prec]))
-    assert mx < TOL_ENC[prec][0] and rms < TOL_ENC[prec][1], (mx, rms)
+    tol = (8e-6, 8e-7) if prec == "fp32" else (8e-3, 1.2e-3)   # per-op path converts operands per call (tf32: truncation)
+    record("per_module", (prec,), [mx, rms], list(tol))
+    assert mx < tol[0] and rms < tol[1], (mx, rms)
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -282,7 +293,7 @@ def test_edge_shapes(dev, prec):
     # empty batch / zero frames
     assert enc(torch.zeros(0, 10, 768, device=dev), None)[0].shape == (0, 10, 768)
     assert enc(torch.zeros(2, 0, 768, device=dev), None)[0].shape == (2, 0, 768)
-    tol = TOL_ENC[prec][0]
+    tol = TOL_EDGE[prec]
     for lengths, masked in [([1], False), ([3, 2], True), ([130, 127, 5], True), ([17, 0], True), ([33], False)]:
         xs = encoder_input(lengths, 768, 99)
         if max(lengths) == 17:            # zero-length utterance: keep T = 17
@@ -309,7 +320,7 @@ def test_weight_refresh_on_parameter_update(dev):
     b = enc(xs, None)[0]
     ref = O.encoder_forward(sd2, xs.cpu().double(), None, 12)
     assert not torch.allclose(a, b)
-    assert err_stats(b.cpu(), ref)[0] < 2e-4
+    assert err_stats(b.cpu(), ref)[0] < 1e-5
 
 
 def test_launch_counter_counts_kernels(dev):
@@ -335,7 +346,7 @@ mask = O.non_pad_mask(c["lengths"]).unsqueeze(1).cuda()
 a = enc(c["xs"].cuda(), mask)[0].cpu(); b = enc(c["xs"].cuda(), mask)[0].cpu()
 mx, rms = err_stats(a, torch.from_numpy(c["z"]["out_f64"]))
 print("SPLITK", mx, rms, bool(torch.equal(a, b)))
-assert mx < 2e-2 and rms < 3e-3 and torch.equal(a, b)
+assert mx < 1.8e-2 and rms < 1.2e-3 and torch.equal(a, b)
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        env=dict(os.environ, AVSR_B200_SPLITK="1"), timeout=300)
@@ -390,8 +401,8 @@ def test_shape_policy_direct_until_seen_then_graph(dev):
         out = enc(xs.to(dev), None)[0].cpu()
         ref = O.encoder_forward(sd, xs.double(), None, 12)
         mx, _ = err_stats(out, ref)
-        record("shape_policy", (T,), mx, TOL_ENC["f16"][0])
-        assert mx < TOL_ENC["f16"][0], (T, mx)
+        record("shape_policy", (T,), mx, TOL_ENC_SHALLOW["f16"][0])
+        assert mx < TOL_ENC_SHALLOW["f16"][0], (T, mx)
     st = enc._engine.stats
     assert st["plans_built"] == 0 and st["graph"] == 0 and st["direct"] == len(Ts), st
     assert len(enc._engine._workspaces) == 1              # one growable direct-launch workspace, not one per shape
@@ -413,8 +424,10 @@ def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
     from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict
     lengths = [48, 31]
     sd = encoder_state_dict(3, num_blocks=2)
+    # magnitudes grow, conditioning does not: the FFN branch is linear up to the ReLU, so scaling its LayerNorm gain and
+    # w_1 by `scale` each multiplies the hidden activations by scale^2 (x64 / x4096) without sharpening any softmax
     for k in list(sd):
-        if (k.endswith(".weight") and ".norm_" in k) or ".w_1.weight" in k or ".linear_v.weight" in k:
+        if k.endswith((".norm_ff.weight", ".norm_ff_macaron.weight", ".w_1.weight", ".w_1.bias", ".linear_v.weight")):
             sd[k] = sd[k] * scale
     xs = encoder_input(lengths, 768, 7) * scale
     ref = O.encoder_forward(sd, xs.double(), lengths, 12)
@@ -425,8 +438,9 @@ def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
     mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
     enc.precision = "tf32"
     mx, rms = err_stats(enc(xs.to(dev), mask)[0].cpu(), ref)
-    record("range_tf32", (scale,), [mx / rscale, rms / rscale], list(TOL_ENC["tf32"]))
-    assert mx < TOL_ENC["tf32"][0] * rscale and rms < TOL_ENC["tf32"][1] * rscale, (scale, mx, rms, rscale)
+    tol = (1e-2, 1.2e-3)            # relative to the output's max-abs; 2 layers with inflated FFN branches
+    record("range_tf32", (scale,), [mx / rscale, rms / rscale], list(tol))
+    assert mx < tol[0] * rscale and rms < tol[1] * rscale, (scale, mx, rms, rscale)
     enc.precision = "f16"
     enc.check_saturation = True
     try:
@@ -438,8 +452,8 @@ def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
         assert torch.isfinite(raw).all()
         return
     mx, rms = err_stats(out, ref)
-    record("range_f16", (scale,), [mx / rscale, rms / rscale], list(TOL_ENC["f16"]))
-    assert mx < TOL_ENC["f16"][0] * rscale and rms < TOL_ENC["f16"][1] * rscale, (scale, mx, rms, rscale)
+    record("range_f16", (scale,), [mx / rscale, rms / rscale], list(tol))
+    assert mx < tol[0] * rscale and rms < tol[1] * rscale, (scale, mx, rms, rscale)
 
 
 def test_saturation_counter_counts(dev):
