@@ -196,7 +196,7 @@ static LnGeom ln_geom(int d) {
     if (const char* e = getenv("AVSR_B200_LN")) { if (sscanf(e, "%dx%d", &g.wpr, &g.rpc) != 2) g = LnGeom{0, 0}; }
     return g;
   }();
-  LnGeom g = env.wpr ? env : LnGeom{2, 2};
+  LnGeom g = env.wpr ? env : LnGeom{2, 4};   // r02 sweep (profiles/r02_ln_sweep.txt): 2x4 best in situ
   (void)d;
   return g;
 }

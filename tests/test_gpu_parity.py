@@ -414,7 +414,7 @@ def test_shape_policy_direct_until_seen_then_graph(dev):
         assert torch.equal(o, outs[0])
 
 
-@pytest.mark.parametrize("scale", [8.0, 64.0])
+@pytest.mark.parametrize("scale", [8.0, 64.0, 1024.0])
 def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
     """fp16 operand stores saturate at +-65504.  With LayerNorm gains, FFN w_1 weights and the input scaled up the
     hidden activations approach / pass that limit: the checked forward must either report it (SaturationError) or the
@@ -438,7 +438,7 @@ def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
     mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
     enc.precision = "tf32"
     mx, rms = err_stats(enc(xs.to(dev), mask)[0].cpu(), ref)
-    tol = (1e-2, 1.2e-3)            # relative to the output's max-abs; 2 layers with inflated FFN branches
+    tol = (2.2e-3, 3.2e-4)          # relative to the output's max-abs (observed 5.4e-4 / 7.9e-5 on B200)
     record("range_tf32", (scale,), [mx / rscale, rms / rscale], list(tol))
     assert mx < tol[0] * rscale and rms < tol[1] * rscale, (scale, mx, rms, rscale)
     enc.precision = "f16"
@@ -457,7 +457,7 @@ def test_fp16_range_saturation_is_detected_or_within_tolerance(dev, scale):
 
 
 def test_saturation_counter_counts(dev):
-    """A weight set that certainly overflows half (w_1 x 4096) must trip the counter; the unscaled one must not."""
+    """A weight set that certainly overflows half (w_1 x 2^20) must trip the counter; the unscaled one must not."""
     from auto_avsr_b200 import ConformerEncoder
     from auto_avsr_b200.engine import SaturationError
     from auto_avsr_b200.synthetic import encoder_input, encoder_state_dict
@@ -468,7 +468,7 @@ def test_saturation_counter_counts(dev):
     enc = enc.to(dev).eval()
     enc.check_saturation = True
     enc(xs, None)                                          # in range: no exception
-    sd["encoders.0.feed_forward.w_1.weight"] = sd["encoders.0.feed_forward.w_1.weight"] * 4096.0
+    sd["encoders.0.feed_forward.w_1.weight"] = sd["encoders.0.feed_forward.w_1.weight"] * float(2 ** 20)
     enc.load_state_dict(sd)
     with pytest.raises(SaturationError):
         enc(xs, None)
