@@ -142,6 +142,23 @@ def main() -> None:
         tot += ex / steps
     P(f"  {'sum of exposed':<44s} {tot:>8.1f} us / forward")
 
+    # ---- per-CTA residency of the attention kernel: how long a CTA lives and how many share an SM at a time
+    att = rec[rec[:, 0] == 300]
+    if len(att):
+        life = (att[:, 15] - att[:, 3]) / 1e3
+        work = (att[:, 15] - att[:, 14]) / 1e3
+        P("")
+        P(f"attention_f16 CTAs: open->done median {np.median(life):.2f} us (p90 {np.percentile(life, 90):.2f}), "
+          f"dep->done median {np.median(work):.2f} us (p90 {np.percentile(work, 90):.2f})")
+        g = len(att) // (12 * steps)
+        one = att[np.argsort(att[:, 3], kind="stable")][:g]          # first launch
+        conc = []
+        for r in one:
+            same = one[one[:, 2] == r[2]]
+            conc.append(int(((same[:, 3] < r[15]) & (same[:, 15] > r[3])).sum()))
+        P(f"  first launch: {g} CTAs on {len(set(one[:, 2].tolist()))} SMs; CTAs alive on the same SM during a CTA's life: "
+          f"median {int(np.median(conc))}, max {max(conc)}")
+
     # ---- intra-CTA phases (clock64 deltas)
     keys = sorted({(int(r[0]), int(r[1] >> 32)) for r in rec if r[0] in (300,) or 200 <= r[0] < 300})
     for kid, aux in keys:

@@ -172,6 +172,37 @@ def test_relpos_attention(dev, prec):
         assert err_stats(ctx, ref)[0] < tol * max(1.0, ref.abs().max().item()), (B, T, H, lengths)
 
 
+def test_relpos_attention_moving_reference_maximum(dev):
+    """Scores with a wide spread (q, k x3: logits of sd ~9, hundreds of rows whose later key tiles exceed the running
+    reference maximum by more than 2^8) drive the fp16 kernel's rescale-O-in-tensor-memory path in divergent
+    patterns (some rows of a warp move, others do not); S2-sized so that every SM holds two CTAs."""
+    from auto_avsr_b200 import ops
+    g = torch.Generator().manual_seed(15)
+    B, T, H = 4, 400, 12
+    D = H * 64
+    q, k = torch.randn(B, T, D, generator=g) * 3, torch.randn(B, T, D, generator=g) * 3
+    v = torch.randn(B, T, D, generator=g)
+    p = torch.randn(2 * T - 1, D, generator=g)
+    u, vb = torch.randn(H, 64, generator=g) * 0.3, torch.randn(H, 64, generator=g) * 0.3
+    lengths = [400, 333, 7, 129]
+    ln = torch.tensor(lengths, dtype=torch.int32, device=dev)
+    outs = [ops.relpos_attention(q.to(dev), k.to(dev), v.to(dev), p.to(dev), u.to(dev), vb.to(dev), ln, H,
+                                 precision="f16").cpu() for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+    def heads(t):
+        return t.double().view(B, T, H, 64).transpose(1, 2)
+    scores = O.rel_attention_scores(heads(q), heads(k), p.double().view(2 * T - 1, H, 64).transpose(0, 1),
+                                    u.double(), vb.double())
+    pad = torch.arange(T)[None, :] >= torch.tensor(lengths)[:, None]
+    attn = torch.softmax(scores.masked_fill(pad[:, None, None, :], float("-inf")), dim=-1)
+    ref = (attn @ heads(v)).transpose(1, 2).reshape(B, T, D)
+    mx, rms = err_stats(outs[0], ref)
+    record("relpos_attention_moving_ref", (B, T, H), [mx, rms], [6e-2, 4e-3])
+    # logits of magnitude ~30 carry 11-bit operand rounding of ~0.02 absolute: a few % on the sharpest rows
+    assert mx < 6e-2 and rms < 4e-3, (mx, rms)
+
+
 # ------------------------------------------------------------------------------------------ whole encoder
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", ["tiny_ragged", "tiny_k7_nomask", "full2_ragged", "full12_s1", "full12_ragged"])
