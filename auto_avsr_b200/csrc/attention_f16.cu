@@ -117,54 +117,66 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && nkt > 0) {
-      mbar_expect_tx(q_full, 2 * A2_BQ * 128);
-      tma_load_2d(base + A2_QU, &tmQu, 0, bh * T + i0, q_full);
-      tma_load_2d(base + A2_QV, &tmQv, 0, bh * T + i0, q_full);
+    // ------------------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
+    if (nkt > 0) {
+      if (elect_one_sync()) {
+        mbar_expect_tx(q_full, 2 * A2_BQ * 128);
+        tma_load_2d(base + A2_QU, &tmQu, 0, bh * T + i0, q_full);
+        tma_load_2d(base + A2_QV, &tmQv, 0, bh * T + i0, q_full);
+      }
       for (int it = 0; it < nkt; ++it) {
         const int j0 = it * A2_BKV;
         if (it > 0) mbar_wait(s_full, (it - 1) & 1);          // S/G MMAs of the previous tile retired: K, Pband free
-        mbar_expect_tx(kp_full, A2_BKV * 128 + A2_BAND * 128);
-        tma_load_2d(base + A2_K, &tmK, 0, bh * T + j0, kp_full);
-        const int m_lo = j0 - i0 - (A2_BQ - 1) + T - 1;       // first table row of the band (may be < 0: zero fill)
-        tma_load_3d(base + A2_PB, &tmP, 0, m_lo, h, kp_full);
+        if (elect_one_sync()) {
+          mbar_expect_tx(kp_full, A2_BKV * 128 + A2_BAND * 128);
+          tma_load_2d(base + A2_K, &tmK, 0, bh * T + j0, kp_full);
+          const int m_lo = j0 - i0 - (A2_BQ - 1) + T - 1;     // first table row of the band (may be < 0: zero fill)
+          tma_load_3d(base + A2_PB, &tmP, 0, m_lo, h, kp_full);
+        }
         if (it > 0) mbar_wait(o_full, (it - 1) & 1);          // P.V of the previous tile retired: V free
-        mbar_expect_tx(v_full, A2_BKV * 128);
-        tma_load_2d(base + A2_V, &tmV, 0, bh * T + j0, v_full);
+        if (elect_one_sync()) {
+          mbar_expect_tx(v_full, A2_BKV * 128);
+          tma_load_2d(base + A2_V, &tmV, 0, bh * T + j0, v_full);
+        }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && nkt > 0) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    if (nkt > 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(A2_BQ, A2_BKV);
       constexpr uint32_t idesc_g = umma_idesc_f16(A2_BQ, A2_BAND);
       constexpr uint32_t idesc_o = umma_idesc_f16_bmn(A2_BQ, 64);
+      // every operand tile sits at a fixed shared-memory address: the descriptors are loop-invariant
+      const uint64_t d_qv = umma_desc_sw128(base + A2_QV), d_pb = umma_desc_sw128(base + A2_PB);
+      const uint64_t d_qu = umma_desc_sw128(base + A2_QU), d_k = umma_desc_sw128(base + A2_K);
+      const uint64_t d_p = umma_desc_sw128(base + A2_P), d_v = umma_desc_sw128(base + A2_V);
+      const uint32_t t_s = tmem + T2_S, t_g = tmem + T2_G, t_o = tmem + T2_O;
       auto issue_scores = [&]() {
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)   // d_k = 64 halves = 4 MMA-K steps of 32 bytes inside one atom
-          mma_f16(tmem + T2_G, umma_desc_sw128(base + A2_QV + ks * 32), umma_desc_sw128(base + A2_PB + ks * 32),
-                  idesc_g, ks != 0);
+          for (int ks = 0; ks < 4; ++ks)   // d_k = 64 halves = 4 MMA-K steps of 32 bytes (+2 in the 16-byte address field)
+            mma_f16(t_g, d_qv + 2 * ks, d_pb + 2 * ks, idesc_g, ks != 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_f16(tmem + T2_S, umma_desc_sw128(base + A2_QU + ks * 32), umma_desc_sw128(base + A2_K + ks * 32),
-                  idesc_s, ks != 0);
-        tc_commit(s_full);
+          for (int ks = 0; ks < 4; ++ks)
+            mma_f16(t_s, d_qu + 2 * ks, d_k + 2 * ks, idesc_s, ks != 0);
+          tc_commit(s_full);
+        }
       };
       mbar_wait(q_full, 0);
       mbar_wait(kp_full, 0);
       tc_fence_after();
       issue_scores();
-      AVSR_TRACE_MARK(true, trc, 2);
+      AVSR_TRACE_MARK(lane == 0, trc, 2);
       for (int it = 0; it < nkt; ++it) {
         mbar_wait(p_full, it & 1);   // softmax consumed S/G(it), rescaled O if needed and published P(it)
         mbar_wait(v_full, it & 1);
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)   // A = P: K-major, 32 keys = 2 steps of 32 bytes; B = V: 16 key rows (2 KB) per step
-          mma_f16(tmem + T2_O, umma_desc_sw128(base + A2_P + ks * 32), umma_desc_sw128(base + A2_V + ks * (16 * 128)),
-                  idesc_o, (it | ks) != 0);
-        tc_commit(o_full);
+        if (elect_one_sync()) {
+          // A = P: K-major, 32 keys = 2 steps of 32 bytes; B = V: 16 key rows (2 KB = 128 in the address field) per step
+          mma_f16(t_o, d_p, d_v, idesc_o, it != 0);
+          mma_f16(t_o, d_p + 2, d_v + 128, idesc_o, 1);
+          tc_commit(o_full);
+        }
         if (it + 1 < nkt) {
           mbar_wait(kp_full, (it + 1) & 1);
           tc_fence_after();

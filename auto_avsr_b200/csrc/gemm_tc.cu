@@ -159,8 +159,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();   // everything above overlapped the previous kernel's tail; from here on we touch its outputs
   AVSR_TSPAN_DEP();
 
+  // producer / MMA warps: warp-uniform loops, only the instruction issue is guarded by elect.sync (operands stay in
+  // uniform registers; see sm100.cuh elect_one_sync)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int it = 0;                                       // running k-block counter across tiles
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int tile = item % total_tiles, split = item / total_tiles;
@@ -170,17 +172,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-          const uint32_t a_dst = base + s * Cfg::kStageBytes;
+          if (elect_one_sync()) {
+            mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+            const uint32_t a_dst = base + s * Cfg::kStageBytes;
 #pragma unroll
-          for (int ms = 0; ms < MSUB; ++ms)
-            tma_load_2d(a_dst + ms * (TC_BM * 128), &tmA, kb * KE, m0 + ms * TC_BM, full_bar(s));
-          tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * KE, n0, full_bar(s));
+            for (int ms = 0; ms < MSUB; ++ms)
+              tma_load_2d(a_dst + ms * (TC_BM * 128), &tmA, kb * KE, m0 + ms * TC_BM, full_bar(s));
+            tma_load_2d(a_dst + Cfg::kABytes, &tmB, kb * KE, n0, full_bar(s));
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = Op::idesc(TC_BM, BN);
       int it = 0, t = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++t) {
@@ -198,16 +202,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = base + s * Cfg::kStageBytes;
           const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int ms = 0; ms < MSUB; ++ms) {
-            const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
+            for (int ms = 0; ms < MSUB; ++ms) {
+              const uint64_t a_desc = umma_desc_sw128(a_addr + ms * (TC_BM * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
-              Op::mma(tacc + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0) || (k != 0));
+              for (int k = 0; k < 4; ++k)  // one MMA-K = 32 bytes = +2 in the descriptor's 16-byte address field
+                Op::mma(tacc + ms * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0) || (k != 0));
+            }
+            tc_commit(empty_bar(s));
+            if (kb == kb1 - 1) tc_commit(tmem_full_bar(acc));
           }
-          tc_commit(empty_bar(s));
         }
-        tc_commit(tmem_full_bar(acc));
       }
     }
   } else {

@@ -147,17 +147,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 0);
+  // Producer and MMA warps run warp-uniform loops and guard only the instruction issue with elect.sync: TMA / tcgen05
+  // operands live in uniform registers, and inside a divergent `lane == 0` region every operand is rebuilt and moved
+  // per instruction (r02 SASS: ~22 instructions + an ELECT / BRA.U.ANY loop per UTCHMMA).
   if constexpr (PREB) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       const int npre = nkb < S ? nkb : S;      // every stage is free on entry: no empty-barrier wait needed
       for (int kb = 0; kb < npre; ++kb) {
-        if (rank == 0) mbar_expect_tx(full_bar(kb), 2 * Cfg::kStageBytes);
-        const uint32_t dst = base + kb * Cfg::kStageBytes;
-        const int kc = (kb0 + kb) * KE;
-        tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kc, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(kb));
-        if constexpr (Cfg::kNSub == 2)
-          tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
-                          n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(kb));
+        if (elect_one_sync()) {
+          if (rank == 0) mbar_expect_tx(full_bar(kb), 2 * Cfg::kStageBytes);
+          const uint32_t dst = base + kb * Cfg::kStageBytes;
+          const int kc = (kb0 + kb) * KE;
+          tma_load_2d_2sm(dst + Cfg::kABytes, &tmB, kc, n0 + (int)rank * (Cfg::kN0 / 2), full_bar(kb));
+          if constexpr (Cfg::kNSub == 2)
+            tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
+                            n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(kb));
+        }
       }
     }
   }
@@ -166,18 +171,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        if constexpr (PREB) {
-          if (kb < S) {                                                   // expect_tx + B already issued before the wait
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (kb / S) & 1;
+      if constexpr (PREB) {
+        if (kb < S) {                                                   // expect_tx + B already issued before the wait
+          if (elect_one_sync())
             tma_load_2d_2sm(base + s * Cfg::kStageBytes, &tmA, (kb0 + kb) * KE, m0 + (int)rank * 128, full_bar(s));
-            AVSR_TRACE_MARK(kb == 0, trc, 2);
-            continue;
-          }
+          AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 2);
+          continue;
         }
-        mbar_wait(empty_bar(s), ph ^ 1);                                  // own stage free (leader's commit, multicast)
+      }
+      mbar_wait(empty_bar(s), ph ^ 1);                                  // own stage free (leader's commit, multicast)
+      if (elect_one_sync()) {
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes); // bytes of BOTH CTAs land on the leader's barrier
         const uint32_t dst = base + s * Cfg::kStageBytes;
         const int kc = (kb0 + kb) * KE;
@@ -187,33 +193,35 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (Cfg::kNSub == 2)
           tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
                           n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(s));
-        AVSR_TRACE_MARK(kb == 0, trc, 2);
       }
-      AVSR_TRACE_MARK(true, trc, 3);
+      AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 2);
     }
+    AVSR_TRACE_MARK(lane == 0, trc, 3);
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      const uint32_t idesc0 = umma_idesc_f16(256, Cfg::kN0);
-      const uint32_t idesc1 = umma_idesc_f16(256, Cfg::kNSub == 2 ? Cfg::kN1 : Cfg::kN0);
+    if (rank == 0) {
+      constexpr uint32_t idesc0 = umma_idesc_f16(256, Cfg::kN0);
+      constexpr uint32_t idesc1 = umma_idesc_f16(256, Cfg::kNSub == 2 ? Cfg::kN1 : Cfg::kN0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        AVSR_TRACE_MARK(kb == 0, trc, 4);
+        AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 4);
         const uint32_t a_addr = base + s * Cfg::kStageBytes;
         const uint64_t a_desc = umma_desc_sw128(a_addr);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int j = 0; j < Cfg::kNSub; ++j) {
-          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + Cfg::sub_brow(j) * 128);
+          for (int j = 0; j < Cfg::kNSub; ++j) {
+            const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + Cfg::sub_brow(j) * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_f16_2sm(tmem_base + Cfg::sub_col(j), a_desc + 2 * k, b_desc + 2 * k, j == 0 ? idesc0 : idesc1, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              mma_f16_2sm(tmem_base + Cfg::sub_col(j), a_desc + 2 * k, b_desc + 2 * k, j == 0 ? idesc0 : idesc1, (kb | k) != 0);
+          }
+          tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
+          if (kb == nkb - 1) tc_commit_2sm(tmem_full_bar);   // accumulator complete: wakes both CTAs' epilogues
         }
-        tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
       }
-      tc_commit_2sm(tmem_full_bar);        // accumulator complete: wakes both CTAs' epilogues
-      AVSR_TRACE_MARK(true, trc, 5);
+      AVSR_TRACE_MARK(lane == 0, trc, 5);
     }
   } else {
     // ---------------------------------------------------------------- epilogue (both CTAs: own 128 rows)

@@ -11,6 +11,20 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (the same one every time).  Code that issues TMA / tcgen05 instructions should be
+// warp-uniform and guard only the issue with this predicate: their operands live in UNIFORM registers, and inside a
+// divergent `if (lane == 0)` region the compiler has to rebuild and move every operand per instruction (r02: ~22
+// instructions and an ELECT / BRA.U.ANY loop around each UTCHMMA, which dominated the attention kernel's MMA latency).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
