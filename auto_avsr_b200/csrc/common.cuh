@@ -182,7 +182,15 @@ enum EpiMode : int {
                    // N == 3D): v into `vt` with the SAME head-major layout   -> (B,H,T,64) each
   EPI_VT = 2,      // A = W_v (m = feature), B = frames (n): v^T                     -> (B,H,64,Tp)
   EPI_GLU = 3,     // interleaved pointwise_cov1: value cols [g*128, +64), gate cols +64 -> out (M, N/2)
-  EPI_POS = 4      // linear_pos of all layers: n = l*D + h*64 + d, m = table row      -> (L,H,Rp,64)
+  EPI_POS = 4,     // linear_pos of all layers: n = l*D + h*64 + d, m = table row      -> (L,H,Rp,64)
+  EPI_LSE = 5      // y = acc + bias[n] as fp32 logits (M, ldo) PLUS per (row, half column tile) log-sum-exp partials over
+                   // the columns n < n_valid -- the ctc_lo projection (two-SM kernel only, gemm_tc2_lse)
+};
+
+// one log-sum-exp partial: running maximum, sum of exp(x - maximum) and first index of the maximum
+struct LsePart {
+  float m, s;
+  int idx, pad;
 };
 
 struct EpiParams {
@@ -199,6 +207,8 @@ struct EpiParams {
   const float* pos_v;
   float* partial;     // split-K: fp32 workspace [splits][M][ldo] for the partial tiles (deterministic fix-up)
   int* counters;      // split-K: one arrival counter per output tile, zero on entry, reset by the last arriver
+  int n_valid;        // LSE: columns >= n_valid are padding (stored, but excluded from the partials)
+  LsePart* lse_part;  // LSE: [2 * tiles_n][M] partials (two epilogue warps per lane quarter split a tile's columns)
   void* qu;           // operand-typed (float for OP_F32/OP_TF32, __half for OP_F16)
   void* qv;
   void* kk;
@@ -335,6 +345,12 @@ extern thread_local bool g_tc2_weights_static;
 int gemm_tc2_splitk(const void* A, const void* Bw, int M, int N, int K, float* partial, int bnp, int nsplit,
                     cudaStream_t st);
 
+// ctc_lo (gemm_tc2.cu): logits[M][ldo] = A Bw^T + bias (fp32; N a multiple of 512, padded columns included) and
+// part[nparts][M] log-sum-exp partials over the columns < n_valid; *nparts = 2 * N / 512.  Needs M >= 256, K % 64 == 0.
+int gemm_tc2_lse(const void* A, const void* Bw, const float* bias, int M, int N, int K, int n_valid, float* logits,
+                 long ldo, LsePart* part, int* nparts, cudaStream_t st);
+int gemm_tc2_lse_ok(int M, int N, int K);
+
 // Residual update folded into a LayerNorm's load: row = x + alpha * (bias + part[0] + part[1] + ... ) (fixed order,
 // so the result does not depend on scheduling); the updated row is written to x_out when that is not already the
 // LayerNorm's own fp32 output.
@@ -352,11 +368,19 @@ int launch_embed_scale(const float* xs, float* x, long n, float scale, cudaStrea
 // `out_kind` is an OperandKind: how y / pe is stored
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st, const LnParts* parts = nullptr);
+// y_f32 = LN(x) as fp32 (may alias x) AND y_op = the same values in operand storage (after_norm feeding ctc_lo)
+int launch_layernorm_dual(const float* x, const float* g, const float* b, float* y_f32, void* y_op, int rows, int d,
+                          int out_kind, cudaStream_t st);
 int launch_layernorm2(const float* x, const float* g1, const float* b1, const float* g2, const float* b2, float* y1,
                       void* y2, int rows, int d, int out_kind, cudaStream_t st, const LnParts* parts = nullptr);
 int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st);
 int launch_dwconv_bn_silu(const float* x, const float* wt /*(K,C)*/, const float* scale, const float* shift, void* y,
                           int B, int T, int C, int K, int out_kind, cudaStream_t st);
+
+// head.cu
+int launch_lse_finish(const float* logits, long ldx, const LsePart* part, int nparts, int rows, float* y, long ldy,
+                      int32_t* best, int n, cudaStream_t st);
+int launch_log_softmax_rows(const float* x, long ldx, float* y, long ldy, int32_t* best, int rows, int n, cudaStream_t st);
 
 // attention: q-side tensors (B,H,T,64), vt (B,H,64,Tp), pos (H,Rp,64) for one layer, ctx (B*T, H*64)
 int attention_simt(const float* qu, const float* qv, const float* kk, const float* vt, const float* pos,

@@ -147,9 +147,10 @@ ln_kernel(const float* x /* may alias y1 / pp.x_out */, const float* __restrict_
       const int c = c0 + i * STEP;
       if (c < nvec) {
         if (NP > 0 && pp.x_out) reinterpret_cast<float4*>(pp.x_out)[rv + c] = v[i];
-        store_kind4(y, (long)row * d + 4 * c, out_kind, (v[i].x - mean) * rstd * gg[i].x + bb[i].x,
-                    (v[i].y - mean) * rstd * gg[i].y + bb[i].y, (v[i].z - mean) * rstd * gg[i].z + bb[i].z,
-                    (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
+        const float4 o = make_float4((v[i].x - mean) * rstd * gg[i].x + bb[i].x, (v[i].y - mean) * rstd * gg[i].y + bb[i].y,
+                                     (v[i].z - mean) * rstd * gg[i].z + bb[i].z, (v[i].w - mean) * rstd * gg[i].w + bb[i].w);
+        if (y1) reinterpret_cast<float4*>(y1)[rv + c] = o;       // dual output: the fp32 copy (after_norm -> features)
+        store_kind4(y, (long)row * d + 4 * c, out_kind, o.x, o.y, o.z, o.w);
       }
     }
   } else {
@@ -250,6 +251,11 @@ int launch_layernorm2(const float* x, const float* g1, const float* b1, const fl
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int rows, int d, int out_kind,
                      cudaStream_t st, const LnParts* parts) {
   return launch_ln<false>(x, g, b, nullptr, nullptr, nullptr, y, rows, d, out_kind, st, parts);
+}
+
+int launch_layernorm_dual(const float* x, const float* g, const float* b, float* y_f32, void* y_op, int rows, int d,
+                          int out_kind, cudaStream_t st) {
+  return launch_ln<false>(x, g, b, nullptr, nullptr, y_f32, y_op, rows, d, out_kind, st, nullptr);
 }
 
 // ------------------------------------------------------------------ rel-pos sinusoid table (embedding.py:139-184)

@@ -89,9 +89,9 @@ static int check_cfg(const AvsrEncoderConfig* c) {
 
 // ------------------------------------------------------------------ preparation kernels
 // copy with conversion to an operand storage kind (OP_F32 plain copy, OP_TF32 rounded fp32, OP_F16 half)
-__global__ void copy_round_kernel(const float* __restrict__ src, void* __restrict__ dst, long n, int kind) {
+__global__ void copy_round_kernel(const float* __restrict__ src, void* __restrict__ dst, long n, int kind, float scale) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = src[i];
+    const float v = src[i] * scale;
     if (kind == OP_F16) reinterpret_cast<__half*>(dst)[i] = to_half_sat(v);
     else reinterpret_cast<float*>(dst)[i] = kind == OP_TF32 ? round_tf32(v) : v;
   }
@@ -122,10 +122,11 @@ __global__ void dw_fold_kernel(const float* __restrict__ w, const float* __restr
   shift[c] = bn_b[c] + (b[c] - mean[c]) * s;
 }
 
-static int copy_round(const float* src, void* dst, long n, int kind, cudaStream_t st) {
+static int copy_round(const float* src, void* dst, long n, int kind, cudaStream_t st, float scale = 1.0f) {
+  if (n <= 0) return AVSR_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  copy_round_kernel<<<blocks, 256, 0, st>>>(src, dst, n, kind);
+  copy_round_kernel<<<blocks, 256, 0, st>>>(src, dst, n, kind, scale);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;
 }
@@ -439,6 +440,63 @@ static int plan_branches(int B, int T, int precision) {
   if (want > B) want = B;
   while (want > 1 && (long)(B / want) * T < 256) --want;   // every slice must still feed the two-SM GEMMs (M >= 256)
   return want;
+}
+
+// ------------------------------------------------------------------ the steps either side of the encoder
+// proj_encoder = Linear(idim -> d_model) in front (e2e_asr_conformer.py:31,70), ctc_lo = Linear(d_model -> odim) +
+// log_softmax behind (ctc.py:21,77-84).  Prepared once per parameter update: proj weights in operand storage, both
+// plain and pre-multiplied by sqrt(d_model) (the encoder's embed scale, embedding.py:178, folded into the projection
+// that writes the residual stream); ctc_lo weights in operand storage with odim padded to a multiple of 512 (zero
+// rows; the pair tile of the two-SM GEMM) and the bias padded likewise.
+struct HeadPrep {
+  float *proj_w, *proj_b, *proj_ws, *proj_bs, *ctc_w, *ctc_b;
+  int npad;
+  size_t bytes;
+};
+static HeadPrep layout_head(const AvsrEncoderConfig& c, int idim, int odim, void* base) {
+  HeadPrep H;
+  Carver cv{reinterpret_cast<char*>(base)};
+  const size_t D = c.d_model;
+  H.npad = (int)align_up((size_t)odim, 512);
+  H.proj_w = cv.take(D * idim); H.proj_b = cv.take(D);
+  H.proj_ws = cv.take(D * idim); H.proj_bs = cv.take(D);
+  H.ctc_w = cv.take((size_t)H.npad * D); H.ctc_b = cv.take((size_t)H.npad);
+  H.bytes = cv.off;
+  return H;
+}
+
+struct HeadWorkspace {
+  void* enc;          // the encoder's own workspace (layout_workspace)
+  size_t enc_bytes;
+  float *fx, *logits;
+  LsePart* parts;
+  size_t bytes;
+};
+static HeadWorkspace layout_head_workspace(const AvsrEncoderConfig& c, int B, int T, int idim, int odim, void* base) {
+  HeadWorkspace W;
+  const size_t N = (size_t)B * T;
+  const int npad = (int)align_up((size_t)odim, 512);
+  W.enc = base;
+  W.enc_bytes = align_up(layout_workspace(c, B, T, nullptr).bytes, 256);
+  Carver cv{reinterpret_cast<char*>(base) + W.enc_bytes};
+  W.fx = cv.take(N * (size_t)(idim > c.d_model ? idim : c.d_model));   // operand copy of the features / of hs
+  W.logits = cv.take(N * (size_t)npad);
+  W.parts = reinterpret_cast<LsePart*>(cv.take((size_t)2 * (npad / 512) * N * (sizeof(LsePart) / sizeof(float))));
+  W.bytes = W.enc_bytes + cv.off;
+  return W;
+}
+
+// hs_op (rows, d_model) in operand storage -> logp (rows, odim) fp32 log-probabilities [+ arg max]
+static int ctc_logprobs(const AvsrEncoderConfig& c, const HeadPrep& H, const void* hs_op, int rows, int odim, float* logits,
+                        LsePart* parts, float* logp, int32_t* argmax, int prec, cudaStream_t st) {
+  const int D = c.d_model;
+  if (prec == AVSR_PREC_F16 && gemm_tc2_lse_ok(rows, H.npad, D)) {
+    int nparts = 0;
+    AVSR_TRY(gemm_tc2_lse(hs_op, H.ctc_w, H.ctc_b, rows, H.npad, D, odim, logits, H.npad, parts, &nparts, st));
+    return launch_lse_finish(logits, H.npad, parts, nparts, rows, logp, odim, argmax, odim, st);
+  }
+  AVSR_TRY(run_gemm(prec, EPI_LINEAR, hs_op, H.ctc_w, rows, H.npad, D, epi_linear(rows, H.npad, H.ctc_b, logits, nullptr, 0.f, 0, 0), st));
+  return launch_log_softmax_rows(logits, H.npad, logp, odim, argmax, rows, odim, st);
 }
 
 }  // namespace avsr
@@ -844,6 +902,123 @@ int avsr_pointwise_glu(const float* x, const float* w, const float* b, float* y,
   EpiParams e{};
   e.M = rows; e.N = 2 * C; e.bias = bi; e.out = y; e.ldo = C;
   return run_gemm(precision, EPI_GLU, xa, wi, rows, 2 * C, C, e, st);
+}
+
+size_t avsr_head_prepared_bytes(const AvsrEncoderConfig* cfg, int idim, int odim) {
+  if (check_cfg(cfg) != AVSR_OK || idim <= 0 || odim <= 0) return 0;
+  return layout_head(*cfg, idim, odim, nullptr).bytes;
+}
+
+int avsr_prepare_head(const AvsrEncoderConfig* cfg, int idim, int odim, const float* proj_w, const float* proj_b,
+                      const float* ctc_w, const float* ctc_b, void* prepared_head, size_t prepared_bytes, int precision,
+                      void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(prepared_head && ((proj_w && proj_b) || (ctc_w && ctc_b)), "NULL argument");
+  AVSR_REQUIRE((!proj_w) == (!proj_b) && (!ctc_w) == (!ctc_b), "weight / bias of a projection must be given together");
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  AVSR_REQUIRE(idim > 0 && idim % 8 == 0 && odim > 0, "head: idim=%d must be a positive multiple of 8, odim=%d > 0", idim, odim);
+  HeadPrep H = layout_head(*cfg, idim, odim, prepared_head);
+  if (H.bytes > prepared_bytes) {
+    set_error("prepared head buffer too small: need %zu bytes, got %zu", H.bytes, prepared_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rnd = operand_kind(precision);
+  const long D = cfg->d_model;
+  const float sc = sqrtf((float)cfg->d_model);
+  AVSR_CUDA_TRY(cudaMemsetAsync(prepared_head, 0, H.bytes, st));      // zero rows / bias entries of the odim padding
+  if (proj_w) {   // a module that owns only one of the two projections prepares its half (the other stays zero)
+    AVSR_TRY(copy_round(proj_w, H.proj_w, D * idim, rnd, st)); AVSR_TRY(copy_round(proj_b, H.proj_b, D, 0, st));
+    AVSR_TRY(copy_round(proj_w, H.proj_ws, D * idim, rnd, st, sc)); AVSR_TRY(copy_round(proj_b, H.proj_bs, D, 0, st, sc));
+  }
+  if (ctc_w) {
+    AVSR_TRY(copy_round(ctc_w, H.ctc_w, (long)odim * D, rnd, st)); AVSR_TRY(copy_round(ctc_b, H.ctc_b, odim, 0, st));
+  }
+  return AVSR_OK;
+}
+
+size_t avsr_head_workspace_bytes(const AvsrEncoderConfig* cfg, int B, int T, int idim, int odim) {
+  if (check_cfg(cfg) != AVSR_OK || B < 0 || T < 0 || idim <= 0 || odim <= 0) return 0;
+  if (B == 0 || T == 0) return 256;
+  return layout_head_workspace(*cfg, B, T, idim, odim, nullptr).bytes;
+}
+
+int avsr_proj_encoder(const AvsrEncoderConfig* cfg, const void* prepared_head, const float* feats, int rows, int idim,
+                      int odim, float* y, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(prepared_head && feats && y && workspace, "NULL argument");
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  if (rows <= 0) return AVSR_OK;
+  HeadPrep H = layout_head(*cfg, idim, odim, const_cast<void*>(prepared_head));
+  const size_t need = align_up((size_t)rows * idim * sizeof(float), 256);
+  if (need > workspace_bytes) { set_error("proj_encoder workspace too small: need %zu, got %zu", need, workspace_bytes); return AVSR_E_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const void* fx = feats;
+  if (precision != AVSR_PREC_FP32) { AVSR_TRY(copy_round(feats, workspace, (long)rows * idim, operand_kind(precision), st)); fx = workspace; }
+  return run_gemm(precision, EPI_LINEAR, fx, H.proj_w, rows, cfg->d_model, idim,
+                  epi_linear(rows, cfg->d_model, H.proj_b, y, nullptr, 0.f, 0, 0), st);
+}
+
+size_t avsr_ctc_workspace_bytes(const AvsrEncoderConfig* cfg, int rows, int odim) {
+  if (check_cfg(cfg) != AVSR_OK || rows < 0 || odim <= 0) return 0;
+  const size_t npad = align_up((size_t)odim, 512);
+  return align_up((size_t)rows * cfg->d_model * 4, 256) + align_up((size_t)rows * npad * 4, 256) +
+         align_up((size_t)2 * (npad / 512) * rows * sizeof(LsePart), 256) + 256;
+}
+
+int avsr_ctc_logprobs(const AvsrEncoderConfig* cfg, const void* prepared_head, const float* hs, int rows, int idim,
+                      int odim, float* logp, int32_t* argmax, void* workspace, size_t workspace_bytes, int precision,
+                      void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(prepared_head && hs && (logp || argmax) && workspace, "NULL argument");
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  if (rows <= 0) return AVSR_OK;
+  if (avsr_ctc_workspace_bytes(cfg, rows, odim) > workspace_bytes) {
+    set_error("ctc workspace too small: need %zu, got %zu", avsr_ctc_workspace_bytes(cfg, rows, odim), workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  HeadPrep H = layout_head(*cfg, idim, odim, const_cast<void*>(prepared_head));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Carver cv{reinterpret_cast<char*>(workspace)};
+  float* hx = cv.take((size_t)rows * cfg->d_model);
+  float* logits = cv.take((size_t)rows * H.npad);
+  LsePart* parts = reinterpret_cast<LsePart*>(cv.take((size_t)2 * (H.npad / 512) * rows * (sizeof(LsePart) / sizeof(float))));
+  const void* hs_op = hs;
+  if (precision != AVSR_PREC_FP32) { AVSR_TRY(copy_round(hs, hx, (long)rows * cfg->d_model, operand_kind(precision), st)); hs_op = hx; }
+  return ctc_logprobs(*cfg, H, hs_op, rows, odim, logits, parts, logp, argmax, precision, st);
+}
+
+int avsr_features_to_logprobs(const AvsrEncoderConfig* cfg, const void* prepared, const void* prepared_head,
+                              const float* feats, const int32_t* lengths, int B, int T, int idim, int odim,
+                              float* enc_out, float* logp, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                              int precision, void* stream) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  AVSR_REQUIRE(B >= 0 && T >= 0 && idim > 0 && odim > 0, "bad B=%d T=%d idim=%d odim=%d", B, T, idim, odim);
+  if (B == 0 || T == 0) return AVSR_OK;
+  AVSR_REQUIRE(prepared && prepared_head && feats && (logp || argmax) && workspace, "NULL buffer");
+  AVSR_REQUIRE((long)B * T < (1L << 24), "B*T=%ld too large", (long)B * T);
+  HeadWorkspace HW = layout_head_workspace(*cfg, B, T, idim, odim, workspace);
+  if (HW.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", HW.bytes, workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  Workspace W = layout_workspace(*cfg, B, T, HW.enc);
+  Prepared P = layout_prepared(*cfg, const_cast<void*>(prepared));
+  HeadPrep H = layout_head(*cfg, idim, odim, const_cast<void*>(prepared_head));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int N = B * T, D = cfg->d_model;
+  // (1) proj_encoder with the embed scale folded in, straight into the residual stream: x = sqrt(d) * (f Wp^T + bp)
+  const void* fx = feats;
+  if (precision != AVSR_PREC_FP32) { AVSR_TRY(copy_round(feats, HW.fx, (long)N * idim, operand_kind(precision), st)); fx = HW.fx; }
+  AVSR_TRY(run_gemm(precision, EPI_LINEAR, fx, H.proj_ws, N, D, idim, epi_linear(N, D, H.proj_bs, W.x, nullptr, 0.f, 0, 0), st));
+  // (2) the 12 layers
+  AVSR_TRY(forward_body(*cfg, P, W, B, T, lengths, nullptr, precision, st));
+  // (3) after_norm: fp32 features for the caller (attention decoder / beam search) + the operand of ctc_lo in one pass
+  float* feat_out = enc_out ? enc_out : W.x;
+  AVSR_TRY(launch_layernorm_dual(W.x, P.after_w, P.after_b, feat_out, W.xn, N, D, operand_kind(precision), st));
+  // (4) ctc_lo + log_softmax: GEMM with log-sum-exp partials in its epilogue, one finishing pass
+  return ctc_logprobs(*cfg, H, W.xn, N, odim, HW.logits, HW.parts, logp, argmax, precision, st);
 }
 
 int avsr_rel_sinusoid_table(float* pe, int T, int d, void* stream) {

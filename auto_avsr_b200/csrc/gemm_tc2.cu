@@ -324,6 +324,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
         }
       }
+    } else if constexpr (MODE == EPI_LSE) {                // fp32 logits + log-sum-exp partials of the valid columns
+      float* outp = reinterpret_cast<float*>(ep.out);
+      float rm = -INFINITY, rs = 0.f;                      // this thread's row: running max, sum of exp(x - max)
+      int ri = 0x7fffffff;                                 // first index of the running max
+#pragma unroll 1
+      for (int c = cb; c < ce; c += 32) {
+        float v[32];
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        const float* sb = s_bias + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += sb[j];
+        const int nb = n0 + c;
+        if (nb < ep.n_valid) {
+          const int nv = ep.n_valid - nb;                  // valid columns of this chunk (>= 32: all)
+          float cm = -INFINITY;
+          int ci = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv && v[j] > cm) { cm = v[j]; ci = j; }
+          if (cm > rm) { rs *= __expf(rm - cm); rm = cm; ri = nb + ci; }   // rm = -inf: rs is 0, exp(-inf) = 0
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += (j < nv) ? __expf(v[j] - rm) : 0.f;
+          rs += acc;
+        }
+        stage_write_f32(stg, lane, v, false);
+        __syncwarp();
+        const int n = n0 + c + pc * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = mw + it * 4 + pr;
+          const uint4 pay = stage_read(stg, it, lane);
+          if (m < ep.M && n < ep.N) *reinterpret_cast<uint4*>(outp + (long)m * ep.ldo + n) = pay;
+        }
+        __syncwarp();
+      }
+      const int row = mw + lane;
+      if (row < ep.M) {
+        LsePart pt;
+        pt.m = rm; pt.s = rs; pt.idx = ri; pt.pad = 0;
+        ep.lse_part[(long)((n0 / BNP) * 2 + chalf) * ep.M + row] = pt;
+      }
     } else if (!ep.round_out) {                            // fp32 destination (+ residual)
       float* outp = reinterpret_cast<float*>(ep.out) + (long)split * ep.M * ep.ldo;
 #pragma unroll 1
@@ -477,6 +520,19 @@ int gemm_tc2_splitk(const void* A, const void* Bw, int M, int N, int K, float* p
   if (bnp == 256) return launch_tc2<EPI_LINEAR, 256>(a, b, M, N, K, ep, st, nsplit);
   AVSR_REQUIRE(false, "split-K pair tile %d not instantiated", bnp);
   return AVSR_OK;
+}
+
+int gemm_tc2_lse_ok(int M, int N, int K) { return M >= 256 && N % 512 == 0 && K % 64 == 0 && cdiv(M, 256) * (N / 512) <= 74; }
+
+int gemm_tc2_lse(const void* A, const void* Bw, const float* bias, int M, int N, int K, int n_valid, float* logits,
+                 long ldo, LsePart* part, int* nparts, cudaStream_t st) {
+  AVSR_REQUIRE(gemm_tc2_lse_ok(M, N, K), "gemm_tc2_lse: shape M=%d N=%d K=%d not supported", M, N, K);
+  AVSR_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && n_valid > 0 && n_valid <= N,
+               "gemm_tc2_lse: bad output layout");
+  EpiParams ep{};
+  ep.M = M; ep.N = N; ep.bias = bias; ep.out = logits; ep.ldo = ldo; ep.n_valid = n_valid; ep.lse_part = part;
+  *nparts = 2 * (N / 512);
+  return launch_tc2<EPI_LSE, 512>(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(Bw), M, N, K, ep, st);
 }
 
 // Returns AVSR_OK and sets *handled = 1 when the pair kernel took the GEMM; *handled = 0 -> caller uses gemm_tc.

@@ -5,10 +5,8 @@ from typing import Optional, Tuple
 
 import torch
 
-from .. import ops
 from ..engine import default_precision, require_cuda
-
-_PAD = 128   # the tensor-core GEMMs take N in multiples of 128: ctc_lo's odim (5049) is padded with zero rows
+from ..head import PreparedHead, ctc_log_probs, proj_forward
 
 
 class ProjEncoder(torch.nn.Linear):
@@ -16,12 +14,15 @@ class ProjEncoder(torch.nn.Linear):
     Training / CPU tensors are refused rather than silently computed elsewhere."""
 
     precision: Optional[str] = None
+    _head: Optional[PreparedHead] = None
 
     def forward(self, x):
         if self.training:
             raise NotImplementedError("ProjEncoder: inference forward only on the B200 path (call .eval())")
         require_cuda(x, "ProjEncoder input")
-        return ops.linear(x, self.weight, self.bias, precision=self.precision or default_precision())
+        if self._head is None:
+            self._head = PreparedHead(self.out_features, max(1, self.out_features // 64))
+        return proj_forward(self._head, self, x, self.precision or default_precision())
 
 
 class CTC(torch.nn.Module):
@@ -40,30 +41,19 @@ class CTC(torch.nn.Module):
         self.ignore_id = -1
         self.reduce = reduce
         self.precision: Optional[str] = None
-        self._padded: Optional[Tuple[tuple, torch.Tensor, torch.Tensor]] = None
+        self._head: Optional[PreparedHead] = None
 
     # ------------------------------------------------------------------ helpers
-    def _padded_params(self):
-        """ctc_lo weight / bias with the output dimension padded to a multiple of 128 (zero rows), cached until the
-        parameters change (in-place update -> ``_version``; re-assignment or ``.to()`` -> data_ptr / device)."""
-        w, b = self.ctc_lo.weight, self.ctc_lo.bias
-        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, w.device)
-        if self._padded is None or self._padded[0] != key:
-            odim, k = w.shape
-            npad = (odim + _PAD - 1) // _PAD * _PAD
-            wp = torch.zeros(npad, k, dtype=torch.float32, device=w.device)
-            bp = torch.zeros(npad, dtype=torch.float32, device=w.device)
-            wp[:odim].copy_(w.detach())
-            bp[:odim].copy_(b.detach())
-            self._padded = (key, wp, bp)
-        return self._padded[1], self._padded[2]
-
-    def _logits(self, hs_pad):
+    def _run(self, hs_pad, want_logp=True, want_argmax=False):
+        """ctc_lo GEMM (weights prepared + padded once per parameter update, log-sum-exp partials in its epilogue)
+        followed by one finishing pass -- libavsr_b200 ``avsr_ctc_logprobs``."""
         if self.training:
             raise NotImplementedError("CTC: inference methods only on the B200 path (call .eval())")
         require_cuda(hs_pad, "CTC input")
-        wp, bp = self._padded_params()
-        return ops.linear(hs_pad, wp, bp, precision=self.precision or default_precision())
+        if self._head is None:
+            d = self.ctc_lo.in_features
+            self._head = PreparedHead(d, max(1, d // 64))
+        return ctc_log_probs(self._head, self.ctc_lo, hs_pad, self.precision or default_precision(), want_logp, want_argmax)
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, hs_pad, hlens, ys_pad):
@@ -74,13 +64,13 @@ class CTC(torch.nn.Module):
 
     def log_softmax(self, hs_pad):
         """(B, Tmax, eprojs) -> (B, Tmax, odim) log-probs (ctc.py:77-84)."""
-        return ops.log_softmax(self._logits(hs_pad), self.ctc_lo.out_features)
+        return self._run(hs_pad)[0]
 
     def softmax(self, hs_pad):
         """(B, Tmax, eprojs) -> (B, Tmax, odim) probabilities; also kept in ``self.probs`` (ctc.py:67-75)."""
-        self.probs = ops.log_softmax(self._logits(hs_pad), self.ctc_lo.out_features).exp_()
+        self.probs = self._run(hs_pad)[0].exp_()
         return self.probs
 
     def argmax(self, hs_pad):
         """(B, Tmax, eprojs) -> (B, Tmax) greedy token ids (ctc.py:86-93)."""
-        return ops.argmax_rows(self._logits(hs_pad), self.ctc_lo.out_features)
+        return self._run(hs_pad, want_logp=False, want_argmax=True)[1]

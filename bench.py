@@ -342,6 +342,49 @@ def extras(dev, enc, args, peaks):
                         "frac_of_bf16_sustained_peak": (fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"])
                         if peaks.get("bf16_tflops_sustained") else None}
     log(f"extras: sustained {ms:.3f} ms/step over {n * ms * 1e-3:.1f} s")
+    # BASELINE.json configs[2]: front-end features -> proj_encoder -> encoder -> CTC log-probs (the fused call of
+    # auto_avsr_b200.head); frames/s of the whole chain, device-resident synthetic features
+    try:
+        from auto_avsr_b200 import CTC, ProjEncoder
+        from auto_avsr_b200.head import features_to_log_probs
+        from auto_avsr_b200.synthetic import frontend_features, head_state_dict
+        hsd = head_state_dict(0)
+        proj = ProjEncoder(512, CFG["d_model"])
+        proj.load_state_dict({"weight": hsd["proj_encoder.weight"], "bias": hsd["proj_encoder.bias"]})
+        ctc = CTC(5049, CFG["d_model"], 0.1)
+        ctc.load_state_dict({"ctc_lo.weight": hsd["ctc.ctc_lo.weight"], "ctc_lo.bias": hsd["ctc.ctc_lo.bias"]})
+        proj, ctc = proj.to(dev).eval(), ctc.to(dev).eval()
+        feats = frontend_features(lengths, 512, 4321).to(dev)
+        with torch.no_grad():
+            for _ in range(5):
+                features_to_log_probs(proj, enc, ctc, feats, mask)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                features_to_log_probs(proj, enc, ctc, feats, mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_f = e0.elapsed_time(e1) / 20
+            for _ in range(3):
+                ctc.log_softmax(enc(proj(feats), mask)[0])
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                ctc.log_softmax(enc(proj(feats), mask)[0])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_m = e0.elapsed_time(e1) / 20
+        out["configs2_features_to_ctc_logprobs"] = {
+            "what": "BASELINE.json configs[2] (ASR Conformer-base encoder fwd + CTC head): synthetic (4, 400, 512) front-end "
+                    "features -> proj_encoder -> 12-layer encoder -> ctc_lo (5049) + log_softmax; direct launches (no graph)",
+            "fused_call": {"frames_per_s": sum(lengths) / (ms_f * 1e-3), "ms_per_step": ms_f,
+                           "api": "auto_avsr_b200.head.features_to_log_probs -> avsr_features_to_logprobs"},
+            "module_by_module": {"frames_per_s": sum(lengths) / (ms_m * 1e-3), "ms_per_step": ms_m,
+                                 "api": "ctc.log_softmax(encoder(proj_encoder(x), mask)[0]) (drop-in modules, encoder from its CUDA graph)"}}
+        log(f"extras: configs[2] fused {ms_f:.3f} ms, module-by-module {ms_m:.3f} ms")
+    except Exception as e:          # noqa: BLE001
+        out["configs2_features_to_ctc_logprobs"] = {"error": f"{type(e).__name__}: {e}"}
     # eager-PyTorch comparator on the same GPU (cuBLAS / ATen), same weights and inputs: the UNMODIFIED reference
     # modules moved to cuda when oracle/_ref was built, else the torch restatement (oracle/conformer_oracle.py)
     try:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 3
+#define AVSR_ABI_VERSION 4
 
 enum {
   AVSR_OK = 0,
@@ -184,6 +184,41 @@ int avsr_rel_sinusoid_table(float *pe, int T, int d, void *stream);
  * of the row maximum.  x has row stride ldx >= n (the GEMM output may be padded), y row stride ldy >= n; y or argmax
  * may be NULL (not both). */
 int avsr_log_softmax(const float *x, long ldx, float *y, long ldy, int32_t *argmax, int rows, int n, void *stream);
+
+/* Prepared weights of the two projections: proj_encoder = torch.nn.Linear(idim, d_model)
+ * (e2e_asr_conformer.py:31) and ctc.ctc_lo = torch.nn.Linear(d_model, odim) (ctc.py:21), converted ONCE to the
+ * precision's operand storage: proj both plain and pre-multiplied by sqrt(d_model) (the encoder's embed scale,
+ * transformer/embedding.py:178), ctc_lo with odim padded to a multiple of 512 zero rows.  idim % 8 == 0.
+ * proj_w (d_model, idim), proj_b (d_model), ctc_w (odim, d_model), ctc_b (odim): fp32 device pointers; one of the two
+ * pairs may be NULL (a module that owns only that projection prepares its half). */
+size_t avsr_head_prepared_bytes(const AvsrEncoderConfig *cfg, int idim, int odim);
+int avsr_prepare_head(const AvsrEncoderConfig *cfg, int idim, int odim, const float *proj_w, const float *proj_b,
+                      const float *ctc_w, const float *ctc_b, void *prepared_head, size_t prepared_bytes,
+                      int precision, void *stream);
+
+/* E2E's inference path from front-end features to CTC log-probabilities in ONE call
+ * (e2e_asr_conformer.py:70-71 + ctc.py:77-84; lightning.py:70-72 for B = 1, lengths NULL):
+ *   x = proj_encoder(feats) * sqrt(d) -> written by the GEMM epilogue straight into the residual stream,
+ *   12 x EncoderLayer, after_norm -> enc_out (B,T,d_model) fp32 (NULL: not needed) AND ctc_lo's fp16 operand,
+ *   ctc_lo GEMM whose epilogue leaves per-row log-sum-exp partials, one finishing pass -> logp (B,T,odim) fp32,
+ *   argmax (B*T) int32 greedy ids (either may be NULL, not both).
+ * feats (B,T,idim) fp32.  workspace >= avsr_head_workspace_bytes. */
+size_t avsr_head_workspace_bytes(const AvsrEncoderConfig *cfg, int B, int T, int idim, int odim);
+int avsr_features_to_logprobs(const AvsrEncoderConfig *cfg, const void *prepared, const void *prepared_head,
+                              const float *feats, const int32_t *lengths, int B, int T, int idim, int odim,
+                              float *enc_out, float *logp, int32_t *argmax, void *workspace,
+                              size_t workspace_bytes, int precision, void *stream);
+
+/* The two projections on their own, on the prepared weights (what the ProjEncoder / CTC drop-in modules call when the
+ * reference's E2E.forward drives them one by one): y = feats Wp^T + bp (rows, d_model) fp32, workspace >= rows*idim*4;
+ * logp / argmax = log_softmax / arg max of hs Wc^T + bc over odim, hs (rows, d_model) fp32 = the encoder output,
+ * workspace >= avsr_ctc_workspace_bytes. */
+int avsr_proj_encoder(const AvsrEncoderConfig *cfg, const void *prepared_head, const float *feats, int rows, int idim,
+                      int odim, float *y, void *workspace, size_t workspace_bytes, int precision, void *stream);
+size_t avsr_ctc_workspace_bytes(const AvsrEncoderConfig *cfg, int rows, int odim);
+int avsr_ctc_logprobs(const AvsrEncoderConfig *cfg, const void *prepared_head, const float *hs, int rows, int idim,
+                      int odim, float *logp, int32_t *argmax, void *workspace, size_t workspace_bytes,
+                      int precision, void *stream);
 
 #ifdef __cplusplus
 }

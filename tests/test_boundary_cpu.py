@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(syms) <= exported, sorted(set(syms) - exported)
     from auto_avsr_b200 import _cabi
     assert set(_cabi.SIGNATURES) == set(syms)
-    assert _cabi.lib.avsr_abi_version() == _cabi.ABI_VERSION == 3
+    assert _cabi.lib.avsr_abi_version() == _cabi.ABI_VERSION == 4
     assert _cabi.launch_count() == 0
 
 
@@ -171,13 +171,20 @@ def test_head_dropins_keep_the_reference_state_dict_keys_and_refuse_cpu(built):
     ctc.train()
     with pytest.raises(NotImplementedError, match="inference"):
         ctc.log_softmax(torch.zeros(1, 3, 768))
-    # the padded copy of ctc_lo follows parameter updates
-    wp, bp = ctc._padded_params()
-    assert wp.shape == (5120, 768) and bp.shape == (5120,) and float(wp[5049:].abs().sum()) == 0.0
+    # the prepared (padded, operand-typed) copy lives in the library and is rebuilt when a parameter's version moves
+    from auto_avsr_b200.head import PreparedHead
+    w = ctc.ctc_lo.weight
+    fp0 = PreparedHead._fp(w, ctc.ctc_lo.bias)
     with torch.no_grad():
-        ctc.ctc_lo.weight.add_(1.0)
-    wp2, _ = ctc._padded_params()
-    assert torch.equal(wp2[:5049], ctc.ctc_lo.weight.detach()) and wp2 is not wp
+        w.add_(1.0)
+    assert PreparedHead._fp(w, ctc.ctc_lo.bias) != fp0
+    from auto_avsr_b200 import _cabi
+    import ctypes as C
+    cfg = _cabi.EncoderConfig(768, 12, 3072, 12, 31)
+    need = _cabi.lib.avsr_head_prepared_bytes(C.byref(cfg), 512, 5049)
+    assert need >= (2 * 768 * 512 + 5120 * 768) * 2          # two proj copies + ctc_lo padded to 5120 rows
+    assert _cabi.lib.avsr_head_workspace_bytes(C.byref(cfg), 4, 400, 512, 5049) > 1600 * 5120 * 4
+    assert _cabi.lib.avsr_ctc_workspace_bytes(C.byref(cfg), 1600, 5049) > 1600 * 5120 * 4
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")

@@ -118,3 +118,66 @@ assert torch.isfinite(logp).all() and mx < 4e-2 and rms < 6e-3, (mx, rms)
 assert torch.logsumexp(logp.double(), -1).abs().max() < 1e-4          # every frame's distribution is normalised
 print("CHILD-OK")
 """, timeout=900)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
+@pytest.mark.parametrize("name", ["head_tiny", "head_full"])
+def test_fused_features_to_log_probs_match_reference_golden(name, prec):
+    """ONE library call (avsr_features_to_logprobs): proj_encoder with the embed scale folded in writing the residual
+    stream, the encoder, after_norm emitting ctc_lo's operand, ctc_lo with log-sum-exp partials -- against the fixtures
+    generated from the reference's own proj_encoder / ConformerEncoder / CTC modules."""
+    run_child(f"""
+from auto_avsr_b200.head import features_to_log_probs
+c = load_head_case({name!r})
+proj, enc, ctc = build(c, {prec!r})
+mask = O.non_pad_mask(c["lengths"]).unsqueeze(1).to(dev)
+with torch.no_grad():
+    hs, logp, best = features_to_log_probs(proj, enc, ctc, c["feats"].to(dev), mask, want_argmax=True)
+    hs2, logp2, _ = features_to_log_probs(proj, enc, ctc, c["feats"].to(dev), mask, want_features=False)
+z = c["z"]
+assert hs2 is None and torch.equal(logp, logp2)
+mx, rms = err_stats(hs.cpu(), torch.from_numpy(z["enc_f64"]))
+record("fused_enc", ({name!r}, {prec!r}), [mx, rms], list(TOL[{prec!r}]))
+assert mx < TOL[{prec!r}][0] and rms < TOL[{prec!r}][1], ("enc", mx, rms)
+mx, rms = err_stats(logp.cpu(), torch.from_numpy(z["logp_f64"]))
+record("fused_logp", ({name!r}, {prec!r}), [mx, rms], [TOL[{prec!r}][0] * 2, TOL[{prec!r}][1] * 2])
+assert mx < TOL[{prec!r}][0] * 2 and rms < TOL[{prec!r}][1] * 2, ("logp", mx, rms)
+assert torch.logsumexp(logp.double().cpu(), -1).abs().max() < 1e-4
+assert torch.equal(best.cpu(), logp.argmax(-1).cpu())
+agree = (best.cpu() == torch.from_numpy(z["argmax_f64"])).float().mean().item()
+assert agree >= (0.99 if {prec!r} == "fp32" else 0.9), agree
+print("CHILD-OK")
+""")
+
+
+def test_fused_full_size_s2_matches_module_path_and_oracle():
+    """BASELINE.json configs[2] at full size (4 x 400 frames, idim 512, odim 5049): the fused call (two-SM ctc_lo GEMM
+    with the log-sum-exp epilogue: M = 1600 >= 256) against the module-by-module path and the CPU oracle."""
+    run_child("""
+from auto_avsr_b200.head import features_to_log_probs
+from auto_avsr_b200.synthetic import SHAPES, encoder_state_dict, frontend_features, head_state_dict
+lengths = list(SHAPES["S2r"])
+c = dict(cfg=dict(idim=512, d_model=768, n_heads=12, linear_units=3072, num_blocks=12, cnn_kernel=31, odim=5049),
+         enc_sd=encoder_state_dict(0), head_sd=head_state_dict(0))
+feats = frontend_features(lengths, 512, 4321)
+proj, enc, ctc = build(c, "f16")
+mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+with torch.no_grad():
+    hs, logp, best = features_to_log_probs(proj, enc, ctc, feats.to(dev), mask, want_argmax=True)
+    hs_m, _ = enc(proj(feats.to(dev)), mask)
+    logp_m = ctc.log_softmax(hs_m)
+    best_m = ctc.argmax(hs_m)
+mx, rms = err_stats(hs.cpu(), hs_m.cpu())
+record("fused_vs_modules_enc", ("S2r",), [mx, rms], [1.8e-2, 1.2e-3])
+assert mx < 1.8e-2 and rms < 1.2e-3, (mx, rms)          # proj rounding differs (scale folded before fp16 rounding)
+mx, rms = err_stats(logp.cpu(), logp_m.cpu())
+record("fused_vs_modules_logp", ("S2r",), [mx, rms], [4e-2, 3e-3])
+assert mx < 4e-2 and rms < 3e-3, (mx, rms)
+assert torch.logsumexp(logp.double().cpu(), -1).abs().max() < 1e-4
+assert torch.equal(best.cpu(), logp.argmax(-1).cpu()) and torch.equal(best_m.cpu(), logp_m.argmax(-1).cpu())
+ref = HO.features_to_log_probs(c["head_sd"], c["enc_sd"], feats.float(), lengths, 12)
+mx, rms = err_stats(logp.cpu(), ref)
+record("fused_full_logp_vs_oracle", ("S2r",), [mx, rms], [4e-2, 6e-3])
+assert torch.isfinite(logp).all() and mx < 4e-2 and rms < 6e-3, (mx, rms)
+print("CHILD-OK")
+""", timeout=900)
