@@ -24,7 +24,10 @@ from auto_avsr_b200 import ops, ConformerEncoder, CTC, ProjEncoder
 from oracle import conformer_oracle as O
 from oracle import head_oracle as HO
 dev = torch.device("cuda:0")
-TOL = {{"fp32": (3e-4, 3e-5), "tf32": (2e-2, 3e-3), "f16": (2e-2, 3e-3)}}     # tightened per case below once observed
+# <= 4x the errors observed on B200 (round 2): encoder features, CTC log-probs (max-abs, rms), proj (relative max)
+TOL = {{"fp32": (2.5e-5, 2.4e-6), "tf32": (9e-3, 1.3e-3), "f16": (9e-3, 1.3e-3)}}
+TOL_LOGP = {{"fp32": (1.4e-5, 2.4e-6), "tf32": (5e-3, 1.1e-3), "f16": (5e-3, 1.1e-3)}}
+TOL_PROJ = {{"fp32": 3e-6, "tf32": 1.1e-3, "f16": 1.1e-3}}
 
 def build(c, prec):
     cfg = c["cfg"]
@@ -85,11 +88,11 @@ with torch.no_grad():
 z = c["z"]
 mx, rms = err_stats(x.cpu(), torch.from_numpy(z["proj_f64"]))
 scale = float(torch.from_numpy(z["proj_f64"]).abs().max())
-record("head_proj", ({name!r}, {prec!r}), mx / max(1.0, scale), TOL[{prec!r}][0])
-assert mx < TOL[{prec!r}][0] * max(1.0, scale), ("proj", mx)
+record("head_proj", ({name!r}, {prec!r}), mx / max(1.0, scale), TOL_PROJ[{prec!r}])
+assert mx < TOL_PROJ[{prec!r}] * max(1.0, scale), ("proj", mx)
 mx, rms = err_stats(logp.cpu(), torch.from_numpy(z["logp_f64"]))
-record("head_logp", ({name!r}, {prec!r}), [mx, rms], [TOL[{prec!r}][0] * 2, TOL[{prec!r}][1] * 2])
-assert mx < TOL[{prec!r}][0] * 2 and rms < TOL[{prec!r}][1] * 2, ("logp", mx, rms)
+record("head_logp", ({name!r}, {prec!r}), [mx, rms], list(TOL_LOGP[{prec!r}]))
+assert mx < TOL_LOGP[{prec!r}][0] and rms < TOL_LOGP[{prec!r}][1], ("logp", mx, rms)
 assert logp.shape == tuple(z["logp_f64"].shape)
 assert (prob.sum(-1).cpu() - 1).abs().max() < 1e-4 and ctc.probs is prob
 agree = (best.cpu() == torch.from_numpy(z["argmax_f64"])).float().mean().item()
@@ -113,8 +116,8 @@ with torch.no_grad():
     logp = ctc.log_softmax(hs).cpu()
 ref = HO.features_to_log_probs(c["head_sd"], c["enc_sd"], feats.float(), lengths, 12)
 mx, rms = err_stats(logp, ref)
-record("head_full_s2_logp", ("f16",), [mx, rms], [4e-2, 6e-3])
-assert torch.isfinite(logp).all() and mx < 4e-2 and rms < 6e-3, (mx, rms)
+record("head_full_s2_logp", ("f16",), [mx, rms], [7e-3, 1.1e-3])
+assert torch.isfinite(logp).all() and mx < 7e-3 and rms < 1.1e-3, (mx, rms)
 assert torch.logsumexp(logp.double(), -1).abs().max() < 1e-4          # every frame's distribution is normalised
 print("CHILD-OK")
 """, timeout=900)
@@ -140,8 +143,8 @@ mx, rms = err_stats(hs.cpu(), torch.from_numpy(z["enc_f64"]))
 record("fused_enc", ({name!r}, {prec!r}), [mx, rms], list(TOL[{prec!r}]))
 assert mx < TOL[{prec!r}][0] and rms < TOL[{prec!r}][1], ("enc", mx, rms)
 mx, rms = err_stats(logp.cpu(), torch.from_numpy(z["logp_f64"]))
-record("fused_logp", ({name!r}, {prec!r}), [mx, rms], [TOL[{prec!r}][0] * 2, TOL[{prec!r}][1] * 2])
-assert mx < TOL[{prec!r}][0] * 2 and rms < TOL[{prec!r}][1] * 2, ("logp", mx, rms)
+record("fused_logp", ({name!r}, {prec!r}), [mx, rms], list(TOL_LOGP[{prec!r}]))
+assert mx < TOL_LOGP[{prec!r}][0] and rms < TOL_LOGP[{prec!r}][1], ("logp", mx, rms)
 assert torch.logsumexp(logp.double().cpu(), -1).abs().max() < 1e-4
 assert torch.equal(best.cpu(), logp.argmax(-1).cpu())
 agree = (best.cpu() == torch.from_numpy(z["argmax_f64"])).float().mean().item()
@@ -171,13 +174,13 @@ mx, rms = err_stats(hs.cpu(), hs_m.cpu())
 record("fused_vs_modules_enc", ("S2r",), [mx, rms], [1.8e-2, 1.2e-3])
 assert mx < 1.8e-2 and rms < 1.2e-3, (mx, rms)          # proj rounding differs (scale folded before fp16 rounding)
 mx, rms = err_stats(logp.cpu(), logp_m.cpu())
-record("fused_vs_modules_logp", ("S2r",), [mx, rms], [4e-2, 3e-3])
-assert mx < 4e-2 and rms < 3e-3, (mx, rms)
+record("fused_vs_modules_logp", ("S2r",), [mx, rms], [5.2e-3, 1e-3])
+assert mx < 5.2e-3 and rms < 1e-3, (mx, rms)
 assert torch.logsumexp(logp.double().cpu(), -1).abs().max() < 1e-4
 assert torch.equal(best.cpu(), logp.argmax(-1).cpu()) and torch.equal(best_m.cpu(), logp_m.argmax(-1).cpu())
 ref = HO.features_to_log_probs(c["head_sd"], c["enc_sd"], feats.float(), lengths, 12)
 mx, rms = err_stats(logp.cpu(), ref)
-record("fused_full_logp_vs_oracle", ("S2r",), [mx, rms], [4e-2, 6e-3])
-assert torch.isfinite(logp).all() and mx < 4e-2 and rms < 6e-3, (mx, rms)
+record("fused_full_logp_vs_oracle", ("S2r",), [mx, rms], [6e-3, 1.1e-3])
+assert torch.isfinite(logp).all() and mx < 6e-3 and rms < 1.1e-3, (mx, rms)
 print("CHILD-OK")
 """, timeout=900)
