@@ -145,6 +145,12 @@ __device__ __forceinline__ __half to_half_sat(float x) {
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
   return __ushort_as_half(r);
 }
+// two floats -> packed IEEE halves (a in the low half), round to nearest, saturating: ONE conversion instruction
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 // store 4 consecutive operand values (dst 16-byte aligned for float, 8-byte aligned for half)
 template <typename TOp>
 __device__ __forceinline__ void store_op4(TOp* dst, float a, float b, float c, float d);

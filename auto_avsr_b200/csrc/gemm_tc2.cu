@@ -70,7 +70,7 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
 
 // A pair tile of width BNP is covered by up to two MMA sub-blocks (UMMA N <= 256): 128 -> {128}, 256 -> {256},
 // 384 -> {256, 128}, 512 -> {256, 256}.  Each CTA stages half of every sub-block's B rows.
-template <int BNP>
+template <int BNP, int MODE = EPI_LINEAR, bool RESID = false>
 struct T2Cfg {
   static constexpr int kNSub = BNP > 256 ? 2 : 1;
   static constexpr int kN0 = BNP > 256 ? 256 : BNP;              // width of sub-block 0
@@ -80,12 +80,17 @@ struct T2Cfg {
   static constexpr int kBBytes = kBRowsTotal * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;          // per CTA
   static constexpr int kVecBytes = 3 * BNP * 4;   // bias / pos_bias_u / pos_bias_v of the tile's columns
-  static constexpr int kFixed = 1024 + 256 + kVecBytes + 8 * T2_STG_WARP;
+  // EPI_LINEAR leaves through TMA stores staged in the pipeline stages (idle once the accumulator is complete) or, with
+  // a residual, in the TMA-prefetched residual tile itself; the other modes keep the transposing staging buffers
+  static constexpr int kStgBytes = MODE == EPI_LINEAR ? 0 : 8 * T2_STG_WARP;
+  static constexpr int kResBytes = RESID ? 128 * BNP * 4 : 0;    // this CTA's 128 x BNP fp32 residual tile
+  static constexpr int kFixed = 1024 + 256 + kVecBytes + kStgBytes + kResBytes;
   static constexpr int kStagesFit = (222 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = BNP <= 128 ? 128 : (BNP <= 256 ? 256 : 512);
   static_assert(kStages >= 2 && BNP % 32 == 0 && BNP <= 512, "bad pair tile");
+  static_assert(MODE != EPI_LINEAR || kStages * kStageBytes >= 8 * 8192, "LINEAR staging (8 warps x 2 x 4 KB) lives in the stages");
   __host__ __device__ static constexpr int sub_n(int j) { return j == 0 ? kN0 : kN1; }
   __host__ __device__ static constexpr int sub_col(int j) { return j == 0 ? 0 : kN0; }          // first tile column
   __host__ __device__ static constexpr int sub_brow(int j) { return j == 0 ? 0 : kN0 / 2; }     // first B smem row
@@ -99,25 +104,30 @@ struct T2Cfg {
 template <int MODE, int BNP, bool RELU, bool RESID, bool PREB = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmB1, int K, int tiles_n, int nsplit, EpiParams ep) {
-  using Cfg = T2Cfg<BNP>;
+                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmRes, int K, int tiles_n, int nsplit, EpiParams ep) {
+  using Cfg = T2Cfg<BNP, MODE, RESID>;
   constexpr int S = Cfg::kStages;
   constexpr int KE = 64;   // halves per 128-byte k-block
   extern __shared__ uint8_t t2_smem_raw[];
   const uint32_t raw = smem_u32(t2_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = t2_smem_raw + (base - raw);
-  const uint32_t bars = base + S * Cfg::kStageBytes;   // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + S * Cfg::kStageBytes + (2 * S + 1) * 8);
-  float* s_bias = reinterpret_cast<float*>(gen + S * Cfg::kStageBytes + 256);
-  uint8_t* stg_base = gen + S * Cfg::kStageBytes + 256 + Cfg::kVecBytes;
+  // [stages][residual tile (RESID)][barriers 256 B][per-column vectors][staging (non-LINEAR modes)]
+  constexpr int kBarOff = S * Cfg::kStageBytes + Cfg::kResBytes;
+  const uint32_t res_base = base + S * Cfg::kStageBytes;
+  const uint32_t bars = base + kBarOff;   // full[S], empty[S], tmem_full, (tmem slot), res_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kBarOff + (2 * S + 1) * 8);
+  const uint32_t res_full_bar = bars + 8u * (2 * S + 2);
+  float* s_bias = reinterpret_cast<float*>(gen + kBarOff + 256);
+  uint8_t* stg_base = gen + kBarOff + 256 + Cfg::kVecBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * S);
 #ifdef AVSR_TRACE
   // phase marks: 0 prologue done, 1 dependency resolved, 2 first TMA issued, 3 last TMA issued, 4 first stage full,
   // 5 last MMA committed, 6 accumulator visible to the epilogue, 7 epilogue warp done, 8 cluster drained
-  unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + S * Cfg::kStageBytes + 192);
+  unsigned long long** trc = reinterpret_cast<unsigned long long**>(gen + kBarOff + 192);
   if (threadIdx.x == 0) AVSR_TRACE_OPEN(trc, 200 + MODE, (unsigned)BNP | ((unsigned)(K / 64 / nsplit) << 16));
 #endif
 
@@ -138,6 +148,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (Cfg::kNSub == 2) tma_prefetch_desc(&tmB1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full_bar, 1);
+    if constexpr (MODE == EPI_LINEAR) { tma_prefetch_desc(&tmOut); if (RESID) tma_prefetch_desc(&tmRes); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(smem_u32(tmem_slot));
@@ -171,6 +183,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
 
   if (warp == 0) {
+    if constexpr (RESID) {
+      // this CTA's 128 x BNP tile of the residual stream (complete before the predecessor started): fetched now, consumed
+      // -- and overwritten in place -- by the epilogue, which stores the updated tile from the same shared memory
+      if (elect_one_sync()) {
+        mbar_expect_tx(res_full_bar, Cfg::kResBytes);
+#pragma unroll
+        for (int j = 0; j < BNP / 32; ++j)
+          tma_load_2d(res_base + j * (128 * 128), &tmRes, n0 + 32 * j, m0 + (int)rank * 128, res_full_bar);
+      }
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (kb / S) & 1;
@@ -368,43 +390,74 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ep.lse_part[(long)((n0 / BNP) * 2 + chalf) * ep.M + row] = pt;
       }
     } else if (!ep.round_out) {                            // fp32 destination (+ residual)
-      float* outp = reinterpret_cast<float*>(ep.out) + (long)split * ep.M * ep.ldo;
+      // lane = accumulator row.  Each 32-column chunk is a [32 rows][128 B] box in the TMA 128-byte swizzle (16-byte piece
+      // j of row r at piece j ^ (r & 7): conflict-free lane-per-row accesses, no padding) that ONE TMA store writes out
+      // (rows >= M clipped by the tensor map) -- no transposing read-back, no per-lane addressing or bounds tests.
+      const int mrow = m0 + (int)rank * 128 + q * 32;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      if constexpr (RESID) {
+        // the chunk's box is the matching piece of the prefetched residual tile: x += alpha * (acc + b) in place
+        mbar_wait(res_full_bar, 0);
 #pragma unroll 1
-      for (int c = cb; c < ce; c += 32) {
-        float v[32];
-        tmem_ld32(trow + c, v);
-        tmem_ld_wait();
-        const float* sb = s_bias + c;
+        for (int c = cb; c < ce; c += 32) {
+          float v[32];
+          tmem_ld32(trow + c, v);
+          uint8_t* box = gen + S * Cfg::kStageBytes + (c >> 5) * (128 * 128) + q * 4096;
+          float4 r[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
-        stage_write_f32(stg, lane, v, false);
-        __syncwarp();
-        const int n = n0 + c + pc * 4;
-        float4 r[8];
-        if (RESID) {
+          for (int j = 0; j < 8; ++j) r[j] = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ sw) << 4));
+          tmem_ld_wait();
+          const float* sb = s_bias + c;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int m = mw + it * 4 + pr;
-            r[it] = (m < ep.M && n < ep.N) ? *reinterpret_cast<const float4*>(ep.resid + (long)m * ep.ldo + n)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j) {
+            r[j].x = fmaf(ep.alpha, v[4 * j] + sb[4 * j], r[j].x); r[j].y = fmaf(ep.alpha, v[4 * j + 1] + sb[4 * j + 1], r[j].y);
+            r[j].z = fmaf(ep.alpha, v[4 * j + 2] + sb[4 * j + 2], r[j].z); r[j].w = fmaf(ep.alpha, v[4 * j + 3] + sb[4 * j + 3], r[j].w);
+            *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ sw) << 4)) = r[j];
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one_sync()) {
+            tma_store_3d(&tmOut, res_base + (c >> 5) * (128 * 128) + q * 4096, n0 + c, mrow, split);
+            tma_store_commit();
           }
         }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int m = mw + it * 4 + pr;
-          const uint4 pay = stage_read(stg, it, lane);
-          float4 o = *reinterpret_cast<const float4*>(&pay);
-          if (RESID) {
-            o.x = r[it].x + ep.alpha * o.x; o.y = r[it].y + ep.alpha * o.y;
-            o.z = r[it].z + ep.alpha * o.z; o.w = r[it].w + ep.alpha * o.w;
+      } else {
+        // staging: two 4 KB boxes per warp in the (now idle) pipeline stages
+        const uint32_t stg0 = base + (uint32_t)(warp - 2) * 8192u;
+#pragma unroll 1
+        for (int c = cb, ci = 0; c < ce; c += 32, ++ci) {
+          float v[32];
+          tmem_ld32(trow + c, v);
+          if (ci >= 2) {                                   // the box is free once its previous store has been read
+            if (elect_one_sync()) tma_store_wait_read_n<1>();
+            __syncwarp();
           }
-          if (m < ep.M && n < ep.N) *reinterpret_cast<float4*>(outp + (long)m * ep.ldo + n) = o;
+          tmem_ld_wait();
+          const float* sb = s_bias + c;
+          uint8_t* box = gen + (warp - 2) * 8192 + (ci & 1) * 4096;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j] + sb[4 * j], v[4 * j + 1] + sb[4 * j + 1], v[4 * j + 2] + sb[4 * j + 2],
+                                   v[4 * j + 3] + sb[4 * j + 3]);
+            if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ sw) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one_sync()) {
+            tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 1) * 4096u, n0 + c, mrow, split);
+            tma_store_commit();
+          }
         }
-        __syncwarp();
       }
+      if (elect_one_sync()) tma_store_wait_read_n<0>();    // shared memory must outlive the stores' reads
     } else {                                               // fp16 operand destination (FFN hidden)
-      // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i is converted, staged and stored
+      // 64-column chunks = [32 rows][128 B] boxes of halves, same staging / TMA-store scheme; the tcgen05.ld of chunk
+      // i+1 is in flight while chunk i is converted and staged
       constexpr int NC = (BNP / 2) / 64;                   // 64-column chunks per warp (4 for the 256x512 pair tile)
+      const int mrow = m0 + (int)rank * 128 + q * 32;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      const uint32_t stg0 = base + (uint32_t)(warp - 2) * 8192u;
       float va[64], vb[64];
       tmem_ld32(trow + cb, va);
       tmem_ld32(trow + cb + 32, va + 32);
@@ -418,19 +471,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld32(trow + c + 64, vn);
           tmem_ld32(trow + c + 96, vn + 32);
         }
-        const float* sb = s_bias + c;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) { v[j] += sb[j]; if (RELU) v[j] = fmaxf(v[j], 0.f); }
-        stage_write_f16(stg, lane, v);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int m = mw + it * 4 + pr, n = n0 + c + pc * 8;
-          const uint4 pay = stage_read(stg, it, lane);
-          if (m < ep.M && n < ep.N) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + (long)m * ep.ldo + n) = pay;
+        if (ci >= 2) {
+          if (elect_one_sync()) tma_store_wait_read_n<1>();
+          __syncwarp();
         }
+        const float* sb = s_bias + c;
+        uint8_t* box = gen + (warp - 2) * 8192 + (ci & 1) * 4096;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = v[8 * j + 2 * e] + sb[8 * j + 2 * e], b = v[8 * j + 2 * e + 1] + sb[8 * j + 2 * e + 1];
+            if (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            pk[e] = pack_half2_sat(a, b);
+          }
+          *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async();
         __syncwarp();
+        if (elect_one_sync()) {
+          tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 1) * 4096u, n0 + c, mrow, split);
+          tma_store_commit();
+        }
       }
+      if (elect_one_sync()) tma_store_wait_read_n<0>();
     }
   }
   AVSR_TRACE_MARK(threadIdx.x == 64, trc, 7);
@@ -455,19 +520,20 @@ static bool preb_enabled() {
 }
 
 template <int MODE, int BNP, bool RELU, bool RESID>
-static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, int grid, int K,
-                        int tiles_n, int nsplit, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = T2Cfg<BNP>;
+static int launch_tc2_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const CUtensorMap& tmOut,
+                        const CUtensorMap& tmRes, int grid, int K, int tiles_n, int nsplit, const EpiParams& ep,
+                        cudaStream_t st) {
+  using Cfg = T2Cfg<BNP, MODE, RESID>;
   AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), Cfg::kSmem);
   const EpiParams& epl = ep;
   if (preb_enabled()) {
     AVSR_SET_MAX_SMEM((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), Cfg::kSmem);
-    AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K,
-                tiles_n, nsplit, epl);
+    AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID, true>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, tmOut,
+                tmRes, K, tiles_n, nsplit, epl);
     return AVSR_OK;
   }
-  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, K, tiles_n,
-              nsplit, epl);
+  AVSR_LAUNCH((gemm_tc2_kernel<MODE, BNP, RELU, RESID>), grid, T2_THREADS, Cfg::kSmem, st, tmA, tmB, tmB1, tmOut, tmRes, K,
+              tiles_n, nsplit, epl);
   return AVSR_OK;
 }
 
@@ -481,13 +547,24 @@ static int launch_tc2(const __half* A, const __half* Bw, int M, int N, int K, co
   AVSR_TRY(make_tmap_2d(&tmB1, Bw, (uint64_t)N, (uint64_t)K, (uint64_t)K, Cfg::kNSub == 2 ? Cfg::kN1 / 2 : Cfg::kN0 / 2, 2));
   const int tiles_m = cdiv(M, 256), tiles_n = cdiv(N, BNP);
   const int grid = 2 * tiles_m * tiles_n * nsplit;
+  CUtensorMap tmOut = tmA, tmRes = tmA;    // only EPI_LINEAR reads them
   if constexpr (MODE == EPI_LINEAR) {
+    // output as a (k-slice, row, column) tensor with [1][32 rows][128 B] store boxes: rows >= M are clipped per slice
+    const int esz = ep.round_out ? 2 : 4;
+    AVSR_TRY(make_tmap_3d(&tmOut, ep.out, (uint64_t)nsplit, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo,
+                          (uint64_t)M * (uint64_t)ep.ldo, 32, esz));
     const bool relu = ep.relu != 0, resid = ep.resid != nullptr;
-    if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
-    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
-    if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
+    if (resid) {
+      AVSR_REQUIRE(!ep.round_out && nsplit == 1 && BNP == 128, "two-SM GEMM: the residual epilogue is fp32, unsplit, 256x128 tiles");
+      AVSR_TRY(make_tmap_2d(&tmRes, ep.resid, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 128, 4));
+    }
+    if constexpr (BNP == 128) {
+      if (relu && resid) return launch_tc2_k<MODE, BNP, true, true>(tmA, tmB, tmB1, tmOut, tmRes, grid, K, tiles_n, nsplit, ep, st);
+      if (resid) return launch_tc2_k<MODE, BNP, false, true>(tmA, tmB, tmB1, tmOut, tmRes, grid, K, tiles_n, nsplit, ep, st);
+    }
+    if (relu) return launch_tc2_k<MODE, BNP, true, false>(tmA, tmB, tmB1, tmOut, tmRes, grid, K, tiles_n, nsplit, ep, st);
   }
-  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, tmB1, grid, K, tiles_n, nsplit, ep, st);
+  return launch_tc2_k<MODE, BNP, false, false>(tmA, tmB, tmB1, tmOut, tmRes, grid, K, tiles_n, nsplit, ep, st);
 }
 
 // Deferred split-K plan for a residual GEMM whose consumer is a LayerNorm (the FFN w_2 projections, K = 3072):
@@ -560,6 +637,7 @@ int gemm_tc2_try(int mode, const void* A, const void* Bw, int M, int N, int K, c
     if (N % cand == 0 && tiles_m * (N / cand) <= 74) { bnp = cand; break; }
   }
   if (!bnp) return AVSR_OK;
+  if (mode == EPI_LINEAR && ep.resid && bnp != 128) return AVSR_OK;   // the residual epilogue exists for 256x128 tiles
   *handled = 1;
   const __half* a = reinterpret_cast<const __half*>(A);
   const __half* b = reinterpret_cast<const __half*>(Bw);
