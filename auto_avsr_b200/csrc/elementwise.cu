@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
     float4 o;
     o.x = fmaf(acc[j].x, sc.x, sh.x); o.y = fmaf(acc[j].y, sc.y, sh.y);
     o.z = fmaf(acc[j].z, sc.z, sh.z); o.w = fmaf(acc[j].w, sc.w, sh.w);
-    if (out_kind == OP_F32) {   // exact path for the fp32 reference mode
+    if (out_kind < 0) {         // raw fp32 (training path: plain conv + bias, or the input-gradient correlation)
+    } else if (out_kind == OP_F32) {   // exact path for the fp32 reference mode
       o.x *= sigmoidf_acc(o.x); o.y *= sigmoidf_acc(o.y); o.z *= sigmoidf_acc(o.z); o.w *= sigmoidf_acc(o.w);
     } else {
       o.x *= sigmoidf_fast(o.x); o.y *= sigmoidf_fast(o.y); o.z *= sigmoidf_fast(o.z); o.w *= sigmoidf_fast(o.w);

@@ -5,10 +5,12 @@ reference (espnet/nets/pytorch_backend/encoder/conformer_encoder.py:19,38,186), 
 (e2e_asr_conformer.py:33-39), ``lightning.py`` and the released checkpoints keep working unchanged;
 only ``forward`` differs: on a CUDA tensor it runs the hand-written sm_100a kernels of libavsr_b200.so.
 
-Scope of this round: inference forward (``eval()``; outputs carry no autograd graph).  Training
-forward/backward (dropout, batch-statistics BatchNorm, SyncBN, DDP) is SURVEY.md section 8f item 2 and raises
-``NotImplementedError`` instead of silently falling back to PyTorch.  CPU tensors raise too: there is
-no CPU path in this package.
+Scope: inference forward (``eval()``: one fused C-ABI call, outputs carry no autograd graph) plus the FIRST SLICE of
+training: ``LayerNorm``, ``PositionwiseFeedForward`` and ``ConvolutionModule`` run forward
+AND backward in libavsr_b200 (auto_avsr_b200/train.py: batch-statistics BatchNorm incl. running-stat update, dgrad /
+wgrad as tensor-core GEMMs, gradients on the original Parameters).  The rel-pos attention backward is not built yet, so
+``RelPositionMultiHeadedAttention`` / ``EncoderLayer`` / ``ConformerEncoder`` still raise ``NotImplementedError`` in
+``train()`` instead of silently falling back to PyTorch.  CPU tensors raise too: there is no CPU path in this package.
 """
 from __future__ import annotations
 
@@ -52,8 +54,15 @@ class ConvolutionModule(torch.nn.Module):
 
     def forward(self, x, residual: Optional[torch.Tensor] = None):
         """x (B, T, C) -> (B, T, C); ``residual`` (extension) is added in the last GEMM's epilogue."""
-        _inference_only(self, "ConvolutionModule")
         prec = self.precision or default_precision()
+        if self.training:
+            # training slice (SURVEY.md 8f #2): batch-statistics BatchNorm, forward and backward in libavsr_b200
+            # (eval mode = the inference kernels below; their outputs carry no autograd graph)
+            if not x.is_cuda:
+                raise RuntimeError("ConvolutionModule: CPU tensor; auto_avsr_b200 has no CPU fallback")
+            from ..train import conv_module_train
+            y = conv_module_train(self, x, prec)
+            return y if residual is None else residual + y
         C = self.pointwise_cov2.weight.size(0)
         g = ops.pointwise_glu(x, self.pointwise_cov1.weight, self.pointwise_cov1.bias, prec)
         h = ops.dwconv_bn_silu(g, self.depthwise_conv.weight, self.depthwise_conv.bias, self.norm.weight,

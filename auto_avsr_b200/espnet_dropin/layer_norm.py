@@ -14,6 +14,12 @@ class LayerNorm(torch.nn.LayerNorm):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("LayerNorm: CPU tensor; auto_avsr_b200 has no CPU fallback")
-        if self.dim == -1:
-            return ops.layernorm(x, self.weight, self.bias)
-        return ops.layernorm(x.transpose(1, -1).contiguous(), self.weight, self.bias).transpose(1, -1)
+        if self.dim != -1:
+            return self._last_dim(x.transpose(1, -1).contiguous()).transpose(1, -1)
+        return self._last_dim(x)
+
+    def _last_dim(self, x):
+        if self.training and torch.is_grad_enabled():
+            from ..train import LayerNormFn          # training slice: forward + backward in libavsr_b200
+            return LayerNormFn.apply(x, self.weight, self.bias)
+        return ops.layernorm(x, self.weight, self.bias)

@@ -20,8 +20,13 @@ class PositionwiseFeedForward(torch.nn.Module):
 
     def forward(self, x, residual: Optional[torch.Tensor] = None, scale: float = 1.0):
         """``residual``/``scale`` (extension): returns residual + scale * ffn(x) from the second GEMM's epilogue."""
-        if self.training:
-            raise NotImplementedError("PositionwiseFeedForward: inference forward only on the B200 path (call .eval())")
         prec = self.precision or default_precision()
+        if self.training:
+            # training slice (SURVEY.md 8f #2): autograd Functions whose forward and backward run in libavsr_b200
+            from ..train import feed_forward_train
+            if not x.is_cuda:
+                raise RuntimeError("PositionwiseFeedForward: CPU tensor; auto_avsr_b200 has no CPU fallback")
+            y = feed_forward_train(self, x, prec)
+            return y if residual is None else residual + scale * y
         h = ops.linear(x, self.w_1.weight, self.w_1.bias, relu=True, precision=prec)
         return ops.linear(h, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale, precision=prec)

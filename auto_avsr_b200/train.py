@@ -1,0 +1,235 @@
+"""Training slice of the encoder path (first slice): ``torch.autograd.Function``s whose forward AND
+backward run in libavsr_b200 -- LayerNorm, Linear (+ReLU) with dgrad / wgrad as the same tcgen05 GEMMs on transposed
+operands, GLU, and the depthwise-conv + BatchNorm(batch statistics) + SiLU block.  Gradients land on the original
+``nn.Parameter``s (autograd accumulates what ``backward`` returns), so DDP hooks, ``clip_grad_norm_`` and AdamW
+(lightning.py:49, train.py:37-41) see them unchanged.  torch supplies device memory, the autograd tape, dropout masks
+and the residual adds; no module falls back to PyTorch arithmetic for its own forward or backward.
+
+Not in this slice: the rel-pos attention backward -- ``RelPositionMultiHeadedAttention`` (and therefore a whole
+``EncoderLayer``) still refuses ``train()``.
+
+Backward GEMMs run with TF32 operands (fp32 range: gradients do not fit fp16's) unless ``precision="fp32"``."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._cabi import check, lib
+from .engine import _ptr, _stream_handle, require_cuda
+
+_WS = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index or 0, _stream_handle(device))
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS[key] = torch.empty(nbytes + nbytes // 4 + 1024, dtype=torch.uint8, device=device)
+    return ws
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().contiguous()
+
+
+def bwd_precision(precision: str) -> str:
+    return "fp32" if precision == "fp32" else "tf32"
+
+
+# ------------------------------------------------------------------------------------------------ raw ops
+def layernorm_bwd(x, gamma, dy):
+    x, gamma, dy = _c(x), _c(gamma), _c(dy)
+    d = x.size(-1)
+    rows = x.numel() // d
+    dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+    ws = _workspace(x.device, int(lib.avsr_train_workspace_bytes(rows, d, 1)))
+    with torch.cuda.device(x.device):
+        check(lib.avsr_layernorm_bwd(x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                     rows, d, ws.data_ptr(), ws.numel(), _stream_handle(x.device)))
+    return dx, dg, db
+
+
+def colsum(y):
+    y = _c(y)
+    cols = y.size(-1)
+    rows = y.numel() // cols
+    out = torch.empty(cols, dtype=torch.float32, device=y.device)
+    ws = _workspace(y.device, 148 * cols * 4 + 1024)
+    with torch.cuda.device(y.device):
+        check(lib.avsr_colsum(y.data_ptr(), out.data_ptr(), rows, cols, ws.data_ptr(), ws.numel(), _stream_handle(y.device)))
+    return out
+
+
+def transpose_padded(x2d, pad_to: int = 32):
+    """(rows, cols) fp32 -> (cols, rows_padded) with zero padding of the new inner dim to a multiple of ``pad_to`` (the
+    tensor-core GEMMs take K in 128-byte blocks)."""
+    x2d = _c(x2d)
+    rows, cols = x2d.shape
+    ld = (rows + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros(cols, ld, dtype=torch.float32, device=x2d.device) if ld != rows else \
+        torch.empty(cols, ld, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        check(lib.avsr_transpose(x2d.data_ptr(), out.data_ptr(), rows, cols, ld, _stream_handle(x2d.device)))
+    return out
+
+
+def relu_bwd(y, dy):
+    y, dy = _c(y), _c(dy)
+    dx = torch.empty_like(dy)
+    with torch.cuda.device(y.device):
+        check(lib.avsr_relu_bwd(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(), _stream_handle(y.device)))
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ autograd functions
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm(d, eps 1e-12) (layer_norm.py:21)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, "LayerNorm input")
+        ctx.save_for_backward(x, weight)
+        return ops.layernorm(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx, dg, db = layernorm_bwd(x, weight, dy)
+        return dx, dg, db
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b), act = identity | ReLU (positionwise_feed_forward.py:28-30, the pointwise convs of
+    conformer_encoder.py:31,35).  Backward: dX = dY W and dW = dY^T X through the same GEMM entry on transposed operands,
+    db = column sums of dY."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool, precision: str):
+        require_cuda(x, "Linear input")
+        w2 = weight.reshape(weight.size(0), -1)          # Conv1d(k=1) weights carry a trailing 1
+        y = ops.linear(x, w2, bias, relu=relu, precision=precision)
+        ctx.relu, ctx.precision, ctx.wshape = relu, precision, weight.shape
+        ctx.save_for_backward(x, w2, y if relu else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2, y = ctx.saved_tensors
+        prec = bwd_precision(ctx.precision)
+        dy = _c(dy)
+        if ctx.relu:
+            dy = relu_bwd(y, dy)
+        n, k = w2.shape
+        dy2, x2 = dy.reshape(-1, n), _c(x).reshape(-1, k)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = transpose_padded(w2, 32)                               # (k, n_padded): dX = dY W = dY (W^T)^T
+            dyp = dy2
+            if wt.size(1) != n:                                         # pad dY's columns like W^T's (zeros contribute 0)
+                dyp = torch.zeros(dy2.size(0), wt.size(1), dtype=torch.float32, device=dy.device)
+                dyp[:, :n] = dy2
+            dx = ops.linear(dyp, wt, None, precision=prec).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            dyt, xt = transpose_padded(dy2, 32), transpose_padded(x2, 32)   # (n, rows_p), (k, rows_p)
+            dw = ops.linear(dyt, xt, None, precision=prec).reshape(ctx.wshape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db, None, None
+
+
+class GluFn(torch.autograd.Function):
+    """F.glu(x, dim=-1) on (…, 2C) (conformer_encoder.py:32 in channel-last layout)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        require_cuda(x, "GLU input")
+        x = _c(x)
+        Cc = x.size(-1) // 2
+        rows = x.numel() // (2 * Cc)
+        y = torch.empty(*x.shape[:-1], Cc, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.avsr_glu_fwd(x.data_ptr(), y.data_ptr(), rows, Cc, _stream_handle(x.device)))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _c(dy)
+        Cc = x.size(-1) // 2
+        rows = x.numel() // (2 * Cc)
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib.avsr_glu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), rows, Cc, _stream_handle(x.device)))
+        return dx
+
+
+class DwConvBnSiluFn(torch.autograd.Function):
+    """depthwise Conv1d + BatchNorm1d (training: batch statistics over all B*T frames, running stats updated in place)
+    + SiLU on (B, T, C) (conformer_encoder.py:33-34)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, bn_w, bn_b, running_mean, running_var, momentum: float, eps: float):
+        require_cuda(x, "conv module input")
+        x, w, b, bn_w, bn_b = _c(x), _c(w), _c(b), _c(bn_w), _c(bn_b)
+        B, T, Cc = x.shape
+        K = w.size(-1)
+        y, conv = torch.empty_like(x), torch.empty_like(x)
+        mean, invstd = torch.empty(Cc, device=x.device), torch.empty(Cc, device=x.device)
+        ws = _workspace(x.device, int(lib.avsr_train_workspace_bytes(B * T, Cc, K)))
+        with torch.cuda.device(x.device):
+            check(lib.avsr_dwconv_bn_silu_train_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), bn_w.data_ptr(), bn_b.data_ptr(),
+                                                    _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
+                                                    y.data_ptr(), conv.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                                    B, T, Cc, K, ws.data_ptr(), ws.numel(), _stream_handle(x.device)))
+        ctx.save_for_backward(x, w, conv, mean, invstd, bn_w, bn_b)
+        ctx.mark_non_differentiable(*[t for t in (running_mean, running_var) if t is not None])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, conv, mean, invstd, bn_w, bn_b = ctx.saved_tensors
+        dy = _c(dy)
+        B, T, Cc = x.shape
+        K = w.size(-1)
+        dx, dw = torch.empty_like(x), torch.empty_like(w)
+        db, dg, dbt = (torch.empty(Cc, device=x.device) for _ in range(3))
+        ws = _workspace(x.device, int(lib.avsr_train_workspace_bytes(B * T, Cc, K)))
+        with torch.cuda.device(x.device):
+            check(lib.avsr_dwconv_bn_silu_train_bwd(x.data_ptr(), w.data_ptr(), conv.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                                    bn_w.data_ptr(), bn_b.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                                    db.data_ptr(), dg.data_ptr(), dbt.data_ptr(), B, T, Cc, K, ws.data_ptr(),
+                                                    ws.numel(), _stream_handle(x.device)))
+        return dx, dw, db, dg, dbt, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ module forwards (train)
+def feed_forward_train(m, x, precision: str):
+    """PositionwiseFeedForward.forward in train mode: w_2(dropout(relu(w_1 x)))."""
+    h = LinearFn.apply(x, m.w_1.weight, m.w_1.bias, True, precision)
+    h = m.dropout(h)
+    return LinearFn.apply(h, m.w_2.weight, m.w_2.bias, False, precision)
+
+
+def conv_module_train(m, x, precision: str):
+    """ConvolutionModule.forward in train mode on (B, T, C): pointwise_cov1 -> GLU -> depthwise + BatchNorm(batch stats)
+    + SiLU -> pointwise_cov2.  ``m.norm`` stays a real BatchNorm1d: its running statistics and num_batches_tracked are
+    updated like torch's (momentum None = cumulative average is not supported here)."""
+    bn = m.norm
+    if type(bn) is not torch.nn.BatchNorm1d:
+        raise NotImplementedError(f"conv_module.norm is {type(bn).__name__}: only torch.nn.BatchNorm1d runs on the B200 "
+                                  "training slice (SyncBatchNorm's cross-rank statistics are a later slice)")
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative moving average) is not supported")
+    h = LinearFn.apply(x, m.pointwise_cov1.weight, m.pointwise_cov1.bias, False, precision)
+    g = GluFn.apply(h)
+    track = bn.track_running_stats and bn.running_mean is not None
+    y = DwConvBnSiluFn.apply(g, m.depthwise_conv.weight, m.depthwise_conv.bias, bn.weight, bn.bias,
+                             bn.running_mean if track else None, bn.running_var if track else None, bn.momentum, bn.eps)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return LinearFn.apply(y, m.pointwise_cov2.weight, m.pointwise_cov2.bias, False, precision)

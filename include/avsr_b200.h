@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 4
+#define AVSR_ABI_VERSION 5
 
 enum {
   AVSR_OK = 0,
@@ -219,6 +219,38 @@ size_t avsr_ctc_workspace_bytes(const AvsrEncoderConfig *cfg, int rows, int odim
 int avsr_ctc_logprobs(const AvsrEncoderConfig *cfg, const void *prepared_head, const float *hs, int rows, int idim,
                       int odim, float *logp, int32_t *argmax, void *workspace, size_t workspace_bytes,
                       int precision, void *stream);
+
+/* ---- training slice (first slice) ------------------------------------------------------------
+ * Backward of the HBM-bound kernels and what a Linear's backward needs around the tensor-core GEMMs (dgrad / wgrad are
+ * avsr_linear on transposed operands).  What they replace is torch.autograd's backward of layer_norm.py:21,
+ * positionwise_feed_forward.py:28-30 and conformer_encoder.py:30-35 under lightning.py:86-94.  All fp32; every
+ * cross-row reduction is two-stage with a fixed order (deterministic).  workspace >= avsr_train_workspace_bytes. */
+size_t avsr_train_workspace_bytes(int rows, int d, int K);
+/* LayerNorm(d, eps 1e-12) backward: dx (rows,d), dgamma (d), dbeta (d) from x, gamma, dy (mean / rstd recomputed) */
+int avsr_layernorm_bwd(const float *x, const float *gamma, const float *dy, float *dx, float *dgamma, float *dbeta,
+                       int rows, int d, void *workspace, size_t workspace_bytes, void *stream);
+/* out[c] = sum over rows of y[r][c] (bias gradients) */
+int avsr_colsum(const float *y, float *out, int rows, int cols, void *workspace, size_t workspace_bytes, void *stream);
+/* dst (cols, ld_dst >= rows) = src (rows, cols)^T; columns [rows, ld_dst) of dst are left untouched (pre-zeroed padding) */
+int avsr_transpose(const float *src, float *dst, int rows, int cols, long ld_dst, void *stream);
+/* dx = dy * (y > 0) */
+int avsr_relu_bwd(const float *y, const float *dy, float *dx, long n, void *stream);
+/* F.glu over channels (conformer_encoder.py:32): in (rows, 2C) -> y (rows, C); and its backward din (rows, 2C) */
+int avsr_glu_fwd(const float *in, float *y, long rows, int C, void *stream);
+int avsr_glu_bwd(const float *in, const float *dy, float *din, long rows, int C, void *stream);
+/* depthwise Conv1d(C,C,K,groups=C)+bias -> BatchNorm1d in TRAINING mode (batch statistics over ALL B*T frames incl.
+ * padding, biased variance for the normalisation, running_mean / running_var (may be NULL) updated with `momentum` and
+ * the unbiased variance, eps as given) -> SiLU (conformer_encoder.py:33-34).  Saves conv_out (B,T,C), save_mean (C),
+ * save_invstd (C) for the backward, which returns dx and the gradients of the conv taps (C,1,K), conv bias, BN weight
+ * and BN bias. */
+int avsr_dwconv_bn_silu_train_fwd(const float *x, const float *w, const float *b, const float *bn_w, const float *bn_b,
+                                  float *running_mean, float *running_var, float momentum, float eps, float *y,
+                                  float *conv_out, float *save_mean, float *save_invstd, int B, int T, int C, int K,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int avsr_dwconv_bn_silu_train_bwd(const float *x, const float *w, const float *conv_out, const float *save_mean,
+                                  const float *save_invstd, const float *bn_w, const float *bn_b, const float *dy,
+                                  float *dx, float *dw, float *db, float *dbn_w, float *dbn_b, int B, int T, int C,
+                                  int K, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

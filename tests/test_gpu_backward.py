@@ -1,0 +1,164 @@
+"""Training slice (first slice) on a B200: forward AND backward of the drop-in LayerNorm,
+PositionwiseFeedForward and ConvolutionModule in train() mode run in libavsr_b200 (auto_avsr_b200/train.py) and must
+reproduce outputs, input gradients, parameter gradients and BatchNorm running statistics of the UNMODIFIED reference
+modules (fixtures tests/golden/train_*.npz from oracle/make_golden_train.py: float64, dropout p = 0).
+
+Bounds: forward like the inference tests; gradients relative to the largest reference gradient entry -- backward GEMMs
+run on TF32 operands (f16 / tf32 precision) or fp32 FMAs (fp32 precision); bounds are <= 4x what a B200 produced."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, err_stats, record
+from auto_avsr_b200.synthetic import encoder_state_dict
+
+pytestmark = pytest.mark.gpu
+
+D, F, K = 768, 3072, 31
+PRECS = ["fp32", "tf32", "f16"]
+TOL_FWD = {"fp32": 2e-5, "tf32": 4e-3, "f16": 4e-3}       # relative to the output's max-abs
+TOL_GRAD = {"fp32": 2e-5, "tf32": 4e-3, "f16": 4e-3}      # relative to the reference gradient's max-abs
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "run with gpurun"
+    import __graft_entry__ as g
+    g.build()
+    return torch.device("cuda:0")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = torch.Generator().manual_seed(int(z["seed"]))
+    x = torch.randn(3, 37, D, generator=g, dtype=torch.float64)
+    r = torch.randn(3, 37, D, generator=g, dtype=torch.float64)
+    sd = encoder_state_dict(int(z["wseed"]), D, 12, F, 1, K)
+    return z, x.float(), r.float(), sd
+
+
+def sub_state(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def rel_err(a, ref):
+    ref = torch.as_tensor(np.asarray(ref)).double()
+    return (a.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+
+
+def check_param_grads(module, z, prec, what):
+    for n, p in module.named_parameters():
+        assert p.grad is not None, n
+        key = "grad_" + n
+        if key in z.files:
+            e = rel_err(p.grad, z[key])
+        else:                                    # big matrices: every 8th row + checksums (oracle/make_golden_train.py)
+            e = rel_err(p.grad[::8], z[key + "__rows8"])
+            cs = z[key + "__checksum"]
+            g = p.grad.double().cpu()
+            got = np.array([g.sum().item(), g.abs().sum().item(), (g ** 2).sum().item()])
+            assert abs(got[1] - cs[1]) <= 2e-3 * cs[1] and abs(got[2] - cs[2]) <= 4e-3 * cs[2], (what, n, got, cs)
+        record("backward_" + what, (prec, n), e, TOL_GRAD[prec])
+        assert e < TOL_GRAD[prec], (what, n, prec, e)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gpu_backward_layernorm(dev, prec):
+    from auto_avsr_b200 import LayerNorm
+    z, x, r, sd = load("train_ln")
+    m = LayerNorm(D)
+    m.load_state_dict(sub_state(sd, "encoders.0.norm_ff."))
+    m = m.to(dev).train()
+    xg = x.to(dev).requires_grad_(True)
+    y = m(xg)
+    (y * r.to(dev)).sum().backward()
+    assert rel_err(y, z["y"]) < 5e-6
+    e = rel_err(xg.grad, z["dx"])
+    record("backward_ln", (prec, "dx"), e, 2e-5)
+    assert e < 2e-5, e                                           # LayerNorm backward is fp32 in every mode
+    for n, key in (("weight", "grad_weight"), ("bias", "grad_bias")):
+        e = rel_err(getattr(m, n).grad, z[key])
+        record("backward_ln", (prec, n), e, 2e-5)
+        assert e < 2e-5, (n, e)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gpu_backward_feed_forward(dev, prec):
+    from auto_avsr_b200 import PositionwiseFeedForward
+    z, x, r, sd = load("train_ffn")
+    m = PositionwiseFeedForward(D, F, 0.0)
+    m.load_state_dict(sub_state(sd, "encoders.0.feed_forward."))
+    m = m.to(dev).train()
+    m.precision = prec
+    xg = x.to(dev).requires_grad_(True)
+    y = m(xg)
+    (y * r.to(dev)).sum().backward()
+    e = rel_err(y, z["y"])
+    record("backward_ffn", (prec, "y"), e, TOL_FWD[prec])
+    assert e < TOL_FWD[prec], e
+    e = rel_err(xg.grad, z["dx"])
+    record("backward_ffn", (prec, "dx"), e, TOL_GRAD[prec])
+    assert e < TOL_GRAD[prec], e
+    check_param_grads(m, z, prec, "ffn")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_gpu_backward_conv_module(dev, prec):
+    from auto_avsr_b200 import ConvolutionModule
+    z, x, r, sd = load("train_conv")
+    m = ConvolutionModule(D, K)
+    m.load_state_dict(sub_state(sd, "encoders.0.conv_module."))
+    m = m.to(dev).train()
+    m.precision = prec
+    xg = x.to(dev).requires_grad_(True)
+    y = m(xg)
+    (y * r.to(dev)).sum().backward()
+    e = rel_err(y, z["y"])
+    record("backward_conv", (prec, "y"), e, TOL_FWD[prec])
+    assert e < TOL_FWD[prec], e
+    e = rel_err(xg.grad, z["dx"])
+    record("backward_conv", (prec, "dx"), e, TOL_GRAD[prec])
+    assert e < TOL_GRAD[prec], e
+    check_param_grads(m, z, prec, "conv")
+    # BatchNorm1d bookkeeping exactly like torch's: running statistics (momentum 0.1, unbiased variance) and the counter
+    assert int(m.norm.num_batches_tracked) == int(z["buf_norm.num_batches_tracked"]) == 1
+    for n in ("running_mean", "running_var"):
+        e = rel_err(getattr(m.norm, n), z["buf_norm." + n])
+        record("backward_conv", (prec, n), e, TOL_FWD[prec])
+        assert e < TOL_FWD[prec], (n, e)
+
+
+def test_train_mode_scope_and_optimizer_step(dev):
+    """Gradients land on the original Parameters (AdamW steps them); what is not in the slice refuses loudly."""
+    from auto_avsr_b200 import ConformerEncoder, PositionwiseFeedForward
+    m = PositionwiseFeedForward(D, F, 0.1).to(dev).train()           # dropout active: just has to run and be finite
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    before = [p.detach().clone() for p in m.parameters()]
+    x = torch.randn(2, 50, D, device=dev)
+    for _ in range(2):
+        opt.zero_grad()
+        loss = m(x).pow(2).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 10.0)        # train.py:41
+        opt.step()
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+    assert all(not torch.equal(a, p.detach()) for a, p in zip(before, m.parameters()))
+    enc = ConformerEncoder(num_blocks=1).to(dev).train()
+    with pytest.raises(NotImplementedError):
+        enc(torch.randn(1, 20, D, device=dev), None)
+
+
+def test_ddp_gradient_allreduce_two_ranks(dev):
+    """Two NCCL ranks (both on cuda:0 when the box has a single GPU is not possible -> needs 2 GPUs; skipped otherwise):
+    DistributedDataParallel over a stack of the slice's modules -- every gradient is produced by libavsr_b200's backward
+    and all-reduced by DDP's hooks on the original Parameters (train.py:37)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "ddp_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DDP-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
