@@ -59,8 +59,6 @@ class RelPositionMultiHeadedAttention(nn.Module):
     def forward(self, query, key, value, pos_emb, mask, residual: Optional[torch.Tensor] = None):
         """query (B,T,d); key/value must be the same tensor (self-attention) or None; pos_emb (1,2T-1,d);
         mask (B,1,T) bool or None.  ``residual`` (extension) is added in the output projection's epilogue."""
-        if self.training:
-            raise NotImplementedError("RelPositionMultiHeadedAttention: inference forward only on the B200 path")
         if self.zero_triu or self.d_k != 64:
             raise NotImplementedError("RelPositionMultiHeadedAttention: zero_triu=False and d_k=64 only")
         for other in (key, value):
@@ -68,6 +66,10 @@ class RelPositionMultiHeadedAttention(nn.Module):
                 raise NotImplementedError("RelPositionMultiHeadedAttention: self-attention only (query is key is value)")
         prec = self.precision or default_precision()
         B, T, _ = query.shape
+        if self.training:                       # forward + backward in libavsr_b200 (auto_avsr_b200/train.py)
+            from ..train import attention_train
+            y = attention_train(self, query, pos_emb, mask, prec)
+            return y if residual is None else residual + y
         q = ops.linear(query, self.linear_q.weight, self.linear_q.bias, precision=prec)
         k = ops.linear(query, self.linear_k.weight, self.linear_k.bias, precision=prec)
         v = ops.linear(query, self.linear_v.weight, self.linear_v.bias, precision=prec)

@@ -102,7 +102,6 @@ class EncoderLayer(torch.nn.Module):
             self.concat_linear = torch.nn.Linear(size + size, size)
 
     def forward(self, x_input, mask, cache=None):
-        _inference_only(self, "EncoderLayer")
         if cache is not None or self.concat_after or not self.normalize_before:
             raise NotImplementedError("EncoderLayer: only normalize_before=True, concat_after=False, cache=None "
                                       "(the configuration auto_avsr instantiates) runs on the B200 path")
@@ -110,6 +109,18 @@ class EncoderLayer(torch.nn.Module):
             x, pos_emb = x_input[0], x_input[1]
         else:
             raise NotImplementedError("EncoderLayer: the B200 path needs the (x, pos_emb) rel-pos input")
+        if self.training:
+            # the reference's schedule with its dropouts (conformer_encoder.py:110-162); every sub-module runs forward and
+            # backward in libavsr_b200, torch adds the residuals and draws the dropout masks
+            if self.macaron_style:
+                x = x + self.ff_scale * self.dropout(self.feed_forward_macaron(self.norm_ff_macaron(x)))
+            x = x + self.dropout(self.self_attn(self.norm_mha(x), None, None, pos_emb, mask))
+            if self.conv_module is not None:
+                x = x + self.dropout(self.conv_module(self.norm_conv(x)))
+            x = x + self.ff_scale * self.dropout(self.feed_forward(self.norm_ff(x)))
+            if self.conv_module is not None:
+                x = self.norm_final(x)
+            return (x, pos_emb), mask
         if self.macaron_style:
             x = self.feed_forward_macaron(self.norm_ff_macaron(x), residual=x, scale=self.ff_scale)
         x = self.self_attn(self.norm_mha(x), None, None, pos_emb, mask, residual=x)
@@ -214,15 +225,27 @@ class ConformerEncoder(torch.nn.Module):
 
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, xs, masks, taps: Optional[torch.Tensor] = None):
-        _inference_only(self, "ConformerEncoder")
         if not self._device_path_ok:
             raise NotImplementedError("ConformerEncoder: only the auto_avsr configuration (normalize_before, macaron, "
                                       "cnn module, d_k = 64, zero_triu=False) runs on the B200 path")
         if not xs.is_cuda:
             raise RuntimeError("ConformerEncoder.forward: input is on the CPU; auto_avsr_b200 has no CPU fallback -- "
                                "move the encoder and its input to a CUDA (B200) device")
-        torch.empty(len(self.encoders)).uniform_()     # the reference draws these CPU uniforms every call (repeat.py:23)
         precision = self.precision or default_precision()
+        if self.training:
+            # training: module by module under autograd, every module's forward AND backward in
+            # libavsr_b200 (auto_avsr_b200/train.py); MultiSequential draws the reference's CPU uniforms itself
+            for m in self.modules():
+                if hasattr(m, "precision") and m is not self and m.precision is None:
+                    m.precision = precision
+            xs, masks_ = self.embed(xs), masks
+            xs, masks_ = self.encoders(xs, masks_)
+            if isinstance(xs, tuple):
+                xs = xs[0]
+            if self.normalize_before:
+                xs = self.after_norm(xs)
+            return xs, masks
+        torch.empty(len(self.encoders)).uniform_()     # the reference draws these CPU uniforms every call (repeat.py:23)
         lengths = None if masks is None else mask_to_lengths(masks, xs.size(0), xs.size(1), check=self.check_mask)
         prepared = self._prepared(xs.device, precision)
         out = self._engine.forward(prepared, xs.detach().float(), lengths, precision, use_graph=self.use_graph,

@@ -21,9 +21,9 @@ class RelPositionalEncoding(torch.nn.Module):
         self.max_len = max_len
 
     def forward(self, x: torch.Tensor):
-        if self.training:
-            raise NotImplementedError("RelPositionalEncoding: inference forward only on the B200 path (call .eval())")
         if not x.is_cuda:
             raise RuntimeError("RelPositionalEncoding: CPU tensor; auto_avsr_b200 has no CPU fallback")
         pos_emb = ops.rel_sinusoid_table(x.size(1), self.d_model, x.device).unsqueeze(0)
+        if self.training:      # embedding.py:183-184: both outputs pass through the positional dropout
+            return self.dropout(x * self.xscale), self.dropout(pos_emb)
         return x * self.xscale, pos_emb

@@ -5,8 +5,9 @@ operands, GLU, and the depthwise-conv + BatchNorm(batch statistics) + SiLU block
 (lightning.py:49, train.py:37-41) see them unchanged.  torch supplies device memory, the autograd tape, dropout masks
 and the residual adds; no module falls back to PyTorch arithmetic for its own forward or backward.
 
-Not in this slice: the rel-pos attention backward -- ``RelPositionMultiHeadedAttention`` (and therefore a whole
-``EncoderLayer``) still refuses ``train()``.
+The rel-pos attention core has a (correctness-first, fp32 CUDA-core) backward too, so a whole ``EncoderLayer`` /
+``ConformerEncoder`` runs ``train()``: the reference's layer schedule with its dropouts (conformer_encoder.py:96-170).
+Not built: SyncBatchNorm's cross-rank statistics, dropout on attention probabilities (the reference trains with 0.0).
 
 Backward GEMMs run with TF32 operands (fp32 range: gradients do not fit fp16's) unless ``precision="fp32"``."""
 from __future__ import annotations
@@ -207,6 +208,39 @@ class DwConvBnSiluFn(torch.autograd.Function):
         return dx, dw, db, dg, dbt, None, None, None, None
 
 
+class AttentionCoreFn(torch.autograd.Function):
+    """ctx = softmax(((q+u) k^T + rel_shift((q+v) p^T)) / 8, key mask) v  (attention.py:174-189 + :59-82) on projected
+    q, k, v (B,T,H*64), p (2T-1,H*64).  Forward = the fused attention kernel of the module's precision; backward =
+    avsr_relpos_attention_bwd (fp32, scores recomputed)."""
+
+    @staticmethod
+    def forward(ctx_, q, k, v, p, u, vb, lengths, n_heads: int, precision: str):
+        require_cuda(q, "attention input")
+        out = ops.relpos_attention(q, k, v, p, u, vb, lengths, n_heads, precision=precision)
+        ctx_.save_for_backward(q, k, v, p, u, vb, out, lengths if lengths is not None else torch.empty(0, device=q.device))
+        ctx_.n_heads, ctx_.masked = n_heads, lengths is not None
+        return out
+
+    @staticmethod
+    def backward(ctx_, dctx):
+        q, k, v, p, u, vb, out, lengths = ctx_.saved_tensors
+        q, k, v, p, u, vb, out, dctx = (_c(t) for t in (q, k, v, p, u, vb, out, dctx))
+        B, T, D = q.shape
+        H = ctx_.n_heads
+        dq_k, dq_p, dk, dv = (torch.empty_like(q) for _ in range(4))
+        dp = torch.empty_like(p)
+        ln = lengths.to(torch.int32).contiguous() if ctx_.masked else None
+        ws = _workspace(q.device, int(lib.avsr_relpos_attention_bwd_workspace_bytes(B, T, H)))
+        with torch.cuda.device(q.device):
+            check(lib.avsr_relpos_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), p.data_ptr(), u.data_ptr(),
+                                                vb.data_ptr(), _ptr(ln), out.data_ptr(), dctx.data_ptr(), dq_k.data_ptr(),
+                                                dq_p.data_ptr(), dk.data_ptr(), dv.data_ptr(), dp.data_ptr(), B, T, H,
+                                                ws.data_ptr(), ws.numel(), _stream_handle(q.device)))
+        du = colsum(dq_k.reshape(-1, D)).reshape(u.shape)        # d pos_bias_u = sum over (b, t) of the k part of dq
+        dvb = colsum(dq_p.reshape(-1, D)).reshape(vb.shape)
+        return dq_k + dq_p, dk, dv, dp, du, dvb, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------ module forwards (train)
 def feed_forward_train(m, x, precision: str):
     """PositionwiseFeedForward.forward in train mode: w_2(dropout(relu(w_1 x)))."""
@@ -233,3 +267,19 @@ def conv_module_train(m, x, precision: str):
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return LinearFn.apply(y, m.pointwise_cov2.weight, m.pointwise_cov2.bias, False, precision)
+
+
+def attention_train(m, x, pos_emb, mask, precision: str):
+    """RelPositionMultiHeadedAttention.forward (self-attention) in train mode -> (B, T, d)."""
+    from .espnet_dropin.attention import mask_to_lengths
+    if m.dropout.p > 0:
+        raise NotImplementedError("dropout on the attention probabilities (attention_dropout_rate > 0) is not implemented "
+                                  "in the fused kernel; auto_avsr trains with 0.0 (e2e_asr_conformer.py:33-39)")
+    B, T, D = x.shape
+    q = LinearFn.apply(x, m.linear_q.weight, m.linear_q.bias, False, precision)
+    k = LinearFn.apply(x, m.linear_k.weight, m.linear_k.bias, False, precision)
+    v = LinearFn.apply(x, m.linear_v.weight, m.linear_v.bias, False, precision)
+    p = LinearFn.apply(pos_emb.reshape(2 * T - 1, D), m.linear_pos.weight, None, False, precision)
+    lengths = None if mask is None else mask_to_lengths(mask, B, T)
+    ctx = AttentionCoreFn.apply(q, k, v, p, m.pos_bias_u, m.pos_bias_v, lengths, m.h, precision)
+    return LinearFn.apply(ctx, m.linear_out.weight, m.linear_out.bias, False, precision)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 5
+#define AVSR_ABI_VERSION 6
 
 enum {
   AVSR_OK = 0,
@@ -251,6 +251,17 @@ int avsr_dwconv_bn_silu_train_bwd(const float *x, const float *w, const float *c
                                   const float *save_invstd, const float *bn_w, const float *bn_b, const float *dy,
                                   float *dx, float *dw, float *db, float *dbn_w, float *dbn_b, int B, int T, int C,
                                   int K, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of the rel-pos attention core (avsr_relpos_attention; transformer/attention.py:174-189 + :59-82), fp32:
+ * from q, k, v (B,T,H*64: the projected tensors, biases included), p (2T-1, H*64), pos_bias_u / v (H,64), lengths, the
+ * forward's ctx and the incoming dctx (B,T,H*64) it returns dk, dv, dp and dq in two parts -- dq = dq_k + dq_p, whose
+ * column sums over (b, t) are the gradients of pos_bias_u and pos_bias_v.  Scores are recomputed (nothing of size T^2
+ * is stored); every output element is written by one warp (no atomics). */
+size_t avsr_relpos_attention_bwd_workspace_bytes(int B, int T, int H);
+int avsr_relpos_attention_bwd(const float *q, const float *k, const float *v, const float *p, const float *pos_bias_u,
+                              const float *pos_bias_v, const int32_t *lengths, const float *ctx, const float *dctx,
+                              float *dq_k, float *dq_p, float *dk, float *dv, float *dp, int B, int T, int H,
+                              void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from espnet.nets.pytorch_backend.encoder.conformer_encoder import ConvolutionModule  # noqa: E402
+from espnet.nets.pytorch_backend.encoder.conformer_encoder import ConformerEncoder, ConvolutionModule  # noqa: E402
+from espnet.nets.pytorch_backend.nets_utils import make_non_pad_mask  # noqa: E402
+from espnet.nets.pytorch_backend.transformer.attention import RelPositionMultiHeadedAttention  # noqa: E402
+from espnet.nets.pytorch_backend.transformer.embedding import RelPositionalEncoding  # noqa: E402
 from espnet.nets.pytorch_backend.transformer.layer_norm import LayerNorm  # noqa: E402
 from espnet.nets.pytorch_backend.transformer.positionwise_feed_forward import PositionwiseFeedForward  # noqa: E402
 
@@ -39,13 +42,14 @@ def sub_state(sd, prefix):
     return {k[len(prefix):]: v.double() for k, v in sd.items() if k.startswith(prefix)}
 
 
-def shrink(d):
-    """Big weight-gradient matrices are stored as every 8th row (fp32) plus full-matrix checksums
-    [sum, sum |.|, sum of squares] (float64): keeps the fixtures at ~4 MB instead of 30."""
+def shrink(d, step=8):
+    """Big weight-gradient matrices are stored as every `step`-th row (fp32) plus full-matrix checksums
+    [sum, sum |.|, sum of squares] (float64): keeps the fixtures at a few MB."""
     out = {}
     for k, v in d.items():
         if v.size > 500_000 and k.startswith("grad_"):
-            out[k + "__rows8"] = v[::8].astype(np.float32)
+            out[k + "__rows8"] = v[::step].astype(np.float32)
+            out[k + "__step"] = np.array(step)
             out[k + "__checksum"] = np.array([v.sum(), np.abs(v).sum(), (v.astype(np.float64) ** 2).sum()])
         else:
             out[k] = v
@@ -77,7 +81,43 @@ def main():
     conv = ConvolutionModule(D, K)
     conv.load_state_dict(sub_state(sd, "encoders.0.conv_module."))
     np.savez_compressed(os.path.join(out_dir, "train_conv.npz"), seed=np.array(33), wseed=np.array(21), **shrink(run(conv, x, r)))
-    for n in ("train_ln", "train_ffn", "train_conv"):
+    # ---- rel-pos attention (attention.py:107-193) on a ragged batch, attention dropout 0.0 as E2E builds it
+    LENGTHS = [37, 29, 18]
+    x, r = tensors(34)
+    mask = make_non_pad_mask(LENGTHS).unsqueeze(-2)
+    pos_emb = RelPositionalEncoding(D, 0.0).double().eval()(x)[1]
+    att = RelPositionMultiHeadedAttention(12, D, 0.0).double().train()
+    att.load_state_dict(sub_state(sd, "encoders.0.self_attn."))
+    xg = x.clone().requires_grad_(True)
+    y = att(xg, xg, xg, pos_emb, mask)
+    (y * r).sum().backward()
+    res = dict(y=y.detach().numpy(), dx=xg.grad.numpy(), lengths=np.array(LENGTHS),
+               **{"grad_" + n: p.grad.numpy() for n, p in att.named_parameters()})
+    np.savez_compressed(os.path.join(out_dir, "train_attn.npz"), seed=np.array(34), wseed=np.array(21), **shrink(res))
+    # ---- the whole 2-layer encoder in train mode, every dropout rate 0: output, input gradient, and per-parameter
+    # gradient checksums (+ every 64th row of the big matrices)
+    sd2 = encoder_state_dict(22, D, 12, F, 2, K)
+    enc = ConformerEncoder(attention_dim=D, attention_heads=12, linear_units=F, num_blocks=2, dropout_rate=0.0,
+                           positional_dropout_rate=0.0, attention_dropout_rate=0.0, cnn_module_kernel=K)
+    enc.load_state_dict(sd2, strict=True)
+    enc = enc.double().train()
+    x, r = tensors(35)
+    xg = x.clone().requires_grad_(True)
+    y, _ = enc(xg, mask)
+    (y * r).sum().backward()
+    res = dict(y=y.detach().numpy(), dx=xg.grad.numpy(), lengths=np.array(LENGTHS))
+    for n, p_ in enc.named_parameters():
+        g = p_.grad.numpy()
+        res["cs_" + n] = np.array([g.sum(), np.abs(g).sum(), (g ** 2).sum()])
+        if g.size > 500_000:
+            res["rows64_" + n] = g[::64].astype(np.float32)
+        elif g.size <= 4096:
+            res["grad_" + n] = g
+    for n, b_ in enc.named_buffers():
+        if "running" in n:
+            res["buf_" + n] = b_.detach().numpy()
+    np.savez_compressed(os.path.join(out_dir, "train_enc2.npz"), seed=np.array(35), wseed=np.array(22), **res)
+    for n in ("train_ln", "train_ffn", "train_conv", "train_attn", "train_enc2"):
         print(n, os.path.getsize(os.path.join(out_dir, n + ".npz")) // 1024, "KiB")
 
 

@@ -62,7 +62,8 @@ def check_param_grads(module, z, prec, what):
         if key in z.files:
             e = rel_err(p.grad, z[key])
         else:                                    # big matrices: every 8th row + checksums (oracle/make_golden_train.py)
-            e = rel_err(p.grad[::8], z[key + "__rows8"])
+            step = int(z[key + "__step"]) if key + "__step" in z.files else 8
+            e = rel_err(p.grad[::step], z[key + "__rows8"])
             cs = z[key + "__checksum"]
             g = p.grad.double().cpu()
             got = np.array([g.sum().item(), g.abs().sum().item(), (g ** 2).sum().item()])
@@ -164,6 +165,89 @@ def test_gpu_backward_conv_module(dev, prec):
         assert e < TOL_FWD[prec], (n, e)
 
 
+@pytest.mark.parametrize("prec", PRECS)
+def test_gpu_backward_relpos_attention(dev, prec):
+    """RelPositionMultiHeadedAttention in train() on a ragged batch: the fused forward kernel of the precision, the
+    recomputing fp32 backward kernels, q/k/v/pos/out projections through LinearFn -- against the reference module's
+    autograd (output, dx, all 11 parameter gradients incl. pos_bias_u / pos_bias_v and linear_pos)."""
+    from auto_avsr_b200 import RelPositionMultiHeadedAttention, ops
+    from oracle import conformer_oracle as O
+    z, x, r, sd = load("train_attn")
+    lengths = [int(v) for v in z["lengths"]]
+    m = RelPositionMultiHeadedAttention(12, D, 0.0)
+    m.load_state_dict(sub_state(sd, "encoders.0.self_attn."))
+    m = m.to(dev).train()
+    m.precision = prec
+    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+    pos_emb = ops.rel_sinusoid_table(x.size(1), D, dev).unsqueeze(0)
+    xg = x.to(dev).requires_grad_(True)
+    y = m(xg, None, None, pos_emb, mask)
+    (y * r.to(dev)).sum().backward()
+    e = rel_err(y, z["y"])
+    record("backward_attn", (prec, "y"), e, TOL_FWD[prec])
+    assert e < TOL_FWD[prec], e
+    tol = TOL_GRAD[prec] if prec == "fp32" else 8e-3       # forward probabilities come from fp16 / tf32 operands
+    e = rel_err(xg.grad, z["dx"])
+    record("backward_attn", (prec, "dx"), e, tol)
+    assert e < tol, e
+    for n, p in m.named_parameters():
+        key = "grad_" + n
+        if key in z.files:
+            e = rel_err(p.grad, z[key])
+        else:
+            e = rel_err(p.grad[::int(z[key + "__step"])], z[key + "__rows8"])
+        record("backward_attn", (prec, n), e, tol)
+        assert e < tol, (n, e)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_gpu_backward_whole_encoder_train_mode(dev, prec):
+    """The drop-in ConformerEncoder (2 layers) in train() with every dropout rate 0: forward output, input gradient,
+    every parameter gradient (checksums; rows of the big matrices; small ones in full) and the BatchNorm running
+    statistics against the reference encoder's autograd -- what train.py's training_step drives (lightning.py:86-94)."""
+    from auto_avsr_b200 import ConformerEncoder
+    from oracle import conformer_oracle as O
+    z = np.load(os.path.join(GOLDEN, "train_enc2.npz"))
+    g = torch.Generator().manual_seed(int(z["seed"]))
+    x = torch.randn(3, 37, D, generator=g, dtype=torch.float64).float()
+    r = torch.randn(3, 37, D, generator=g, dtype=torch.float64).float()
+    lengths = [int(v) for v in z["lengths"]]
+    enc = ConformerEncoder(num_blocks=2, dropout_rate=0.0, positional_dropout_rate=0.0, attention_dropout_rate=0.0)
+    enc.load_state_dict(encoder_state_dict(int(z["wseed"]), D, 12, F, 2, K), strict=True)
+    enc = enc.to(dev).train()
+    enc.precision = prec
+    mask = O.non_pad_mask(lengths).unsqueeze(1).to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    y, m_out = enc(xg, mask)
+    assert m_out is mask
+    (y * r.to(dev)).sum().backward()
+    tf, tg = (3e-5, 1e-4) if prec == "fp32" else (8e-3, 4e-2)
+    e = rel_err(y, z["y"])
+    record("backward_enc2", (prec, "y"), e, tf)
+    assert e < tf, e
+    e = rel_err(xg.grad, z["dx"])
+    record("backward_enc2", (prec, "dx"), e, tg)
+    assert e < tg, e
+    worst = 0.0
+    for n, p in enc.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        cs = z["cs_" + n]
+        gd = p.grad.double().cpu()
+        got = np.array([gd.sum().item(), gd.abs().sum().item(), (gd ** 2).sum().item()])
+        if cs[1] > 1e-6:                         # (a bias in front of BatchNorm has a mathematically zero gradient)
+            worst = max(worst, abs(got[1] - cs[1]) / cs[1], abs(got[2] - cs[2]) / cs[2])
+        if "rows64_" + n in z.files:
+            worst = max(worst, rel_err(p.grad[::64], z["rows64_" + n]))
+        elif "grad_" + n in z.files and np.abs(z["grad_" + n]).max() > 1e-9:
+            worst = max(worst, rel_err(p.grad, z["grad_" + n]))
+    record("backward_enc2", (prec, "worst parameter gradient"), worst, tg)
+    assert worst < tg, worst
+    for n, b in enc.named_buffers():
+        if "running" in n:
+            e = rel_err(b, z["buf_" + n])
+            assert e < (1e-5 if prec == "fp32" else 5e-3), (n, e)
+
+
 def test_train_mode_scope_and_optimizer_step(dev):
     """Gradients land on the original Parameters (AdamW steps them); what is not in the slice refuses loudly."""
     from auto_avsr_b200 import ConformerEncoder, PositionwiseFeedForward
@@ -179,9 +263,16 @@ def test_train_mode_scope_and_optimizer_step(dev):
         opt.step()
     assert all(torch.isfinite(p).all() for p in m.parameters())
     assert all(not torch.equal(a, p.detach()) for a, p in zip(before, m.parameters()))
-    enc = ConformerEncoder(num_blocks=1).to(dev).train()
-    with pytest.raises(NotImplementedError):
+    enc = ConformerEncoder(num_blocks=1, attention_dropout_rate=0.1).to(dev).train()
+    with pytest.raises(NotImplementedError):                          # dropout on attention probabilities: not built
         enc(torch.randn(1, 20, D, device=dev), None)
+    enc = ConformerEncoder(num_blocks=1).to(dev).train()             # the reference's rates (0.1 / 0.1 / 0.0)
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-4)
+    out, _ = enc(torch.randn(2, 30, D, device=dev), None)
+    out.pow(2).mean().backward()
+    torch.nn.utils.clip_grad_norm_(enc.parameters(), 10.0)
+    opt.step()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc.parameters())
 
 
 def test_ddp_gradient_allreduce_two_ranks(dev):
