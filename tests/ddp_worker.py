@@ -1,7 +1,6 @@
 """torchrun worker of tests/test_gpu_backward.py::test_ddp_gradient_allreduce_two_ranks (also usable on CPU/gloo for
-the control flow: AVSR_DDP_BACKEND=gloo, then the modules are plain torch stand-ins).  Each rank runs a different
-synthetic bucket through DDP(stack of LayerNorm -> FFN -> LayerNorm -> ConvolutionModule blocks); after backward every
-rank must hold the SAME gradients = the mean of the per-rank gradients (checked against a manual all-reduce of a second,
+Each rank runs a different synthetic, ragged bucket through DistributedDataParallel(ConformerEncoder) in train mode;
+after backward every rank must hold the SAME gradients = the mean of the per-rank gradients (checked against a manual all-reduce of a second,
 un-wrapped replica)."""
 import os
 import sys
@@ -18,28 +17,23 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    from auto_avsr_b200 import ConvolutionModule, LayerNorm, PositionwiseFeedForward
+    from auto_avsr_b200 import ConformerEncoder
 
-    class Block(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.n1, self.ff, self.n2, self.conv = LayerNorm(768), PositionwiseFeedForward(768, 3072, 0.0), LayerNorm(768), \
-                ConvolutionModule(768, 31)
-
-        def forward(self, x):
-            x = x + 0.5 * self.ff(self.n1(x))
-            return x + self.conv(self.n2(x))
-
-    nblocks = int(os.environ.get("AVSR_DDP_BLOCKS", "12"))     # 12 blocks = 113 M parameters = 454 MB of fp32 gradients
+    # the whole 12-layer encoder (170 M parameters = 682 MB of fp32 gradients), dropout off so that the un-wrapped replica
+    # sees the same forward; each rank gets its own bucket (train.py:34-37: one bucket per rank per step)
+    nblocks = int(os.environ.get("AVSR_DDP_BLOCKS", "12"))
+    kw = dict(num_blocks=nblocks, dropout_rate=0.0, positional_dropout_rate=0.0, attention_dropout_rate=0.0)
     torch.manual_seed(0)
-    model = torch.nn.Sequential(*[Block() for _ in range(nblocks)]).to(dev).train()
-    replica = torch.nn.Sequential(*[Block() for _ in range(nblocks)]).to(dev).train()
+    model = ConformerEncoder(**kw).to(dev).train()
+    replica = ConformerEncoder(**kw).to(dev).train()
     replica.load_state_dict(model.state_dict())
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
     g = torch.Generator().manual_seed(100 + rank)
+    lengths = [100, 80 - 10 * rank, 64, 33]
     x = torch.randn(4, 100, 768, generator=g).to(dev)
-    ddp(x).pow(2).mean().backward()
-    replica(x).pow(2).mean().backward()
+    mask = (torch.arange(100, device=dev)[None, :] < torch.tensor(lengths, device=dev)[:, None]).unsqueeze(1)
+    ddp(x, mask)[0].pow(2).mean().backward()
+    replica(x, mask)[0].pow(2).mean().backward()
     nbytes, worst = 0, 0.0
     for (n, p), q in zip(model.named_parameters(), replica.parameters()):
         ref = q.grad.clone()

@@ -192,6 +192,14 @@ def test_gpu_backward_relpos_attention(dev, prec):
     assert e < tol, e
     for n, p in m.named_parameters():
         key = "grad_" + n
+        if key in z.files and np.abs(z[key]).max() < 1e-9:
+            # linear_k.bias: a constant added to every key shifts all scores of a row alike -- softmax ignores it, the
+            # gradient is mathematically zero; absolute check against the scale of the other gradients
+            scale = float(np.abs(z["grad_linear_q.bias"]).max())
+            e = p.grad.abs().max().item() / scale
+            record("backward_attn", (prec, n, "abs / |d linear_q.bias|"), e, tol)
+            assert e < tol, (n, e)
+            continue
         if key in z.files:
             e = rel_err(p.grad, z[key])
         else:
@@ -234,12 +242,19 @@ def test_gpu_backward_whole_encoder_train_mode(dev, prec):
         cs = z["cs_" + n]
         gd = p.grad.double().cpu()
         got = np.array([gd.sum().item(), gd.abs().sum().item(), (gd ** 2).sum().item()])
+        e = 0.0
         if cs[1] > 1e-6:                         # (a bias in front of BatchNorm has a mathematically zero gradient)
-            worst = max(worst, abs(got[1] - cs[1]) / cs[1], abs(got[2] - cs[2]) / cs[2])
-        if "rows64_" + n in z.files:
-            worst = max(worst, rel_err(p.grad[::64], z["rows64_" + n]))
-        elif "grad_" + n in z.files and np.abs(z["grad_" + n]).max() > 1e-9:
-            worst = max(worst, rel_err(p.grad, z["grad_" + n]))
+            e = max(e, abs(got[1] - cs[1]) / cs[1], abs(got[2] - cs[2]) / cs[2])
+        # element-wise only where the gradient is a smooth function of the forward: a hidden unit whose pre-activation
+        # sits within the operand rounding of zero flips its ReLU against the float64 reference and moves its whole row
+        # of d w_1 (the same-mask FFN test above pins that arithmetic); the checksums still cover w_1
+        elementwise = prec == "fp32" or ".w_1." not in n
+        if elementwise and "rows64_" + n in z.files:
+            e = max(e, rel_err(p.grad[::64], z["rows64_" + n]))
+        elif elementwise and "grad_" + n in z.files and np.abs(z["grad_" + n]).max() > 1e-9:
+            e = max(e, rel_err(p.grad, z["grad_" + n]))
+        record("backward_enc2_param", (prec, n), e, tg)
+        worst = max(worst, e)
     record("backward_enc2", (prec, "worst parameter gradient"), worst, tg)
     assert worst < tg, worst
     for n, b in enc.named_buffers():
