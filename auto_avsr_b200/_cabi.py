@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libav
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class AvsrError(RuntimeError):
@@ -92,6 +92,8 @@ SIGNATURES = {
     "avsr_dwconv_bn_silu_train_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "avsr_relpos_attention_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "avsr_relpos_attention_bwd": (_I, [_P] * 14 + [_I, _I, _I, _P, _Z, _P]),
+    "avsr_pack_padded": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "avsr_unpack_padded": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "avsr_head_prepared_bytes": (_Z, [_CFG, _I, _I]),
     "avsr_prepare_head": (_I, [_CFG, _I, _I, _P, _P, _P, _P, _P, _Z, _I, _P]),
     "avsr_head_workspace_bytes": (_Z, [_CFG, _I, _I, _I, _I]),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 6
+#define AVSR_ABI_VERSION 7
 
 enum {
   AVSR_OK = 0,
@@ -262,6 +262,14 @@ int avsr_relpos_attention_bwd(const float *q, const float *k, const float *v, co
                               const float *pos_bias_v, const int32_t *lengths, const float *ctx, const float *dctx,
                               float *dq_k, float *dq_p, float *dk, float *dv, float *dp, int B, int T, int H,
                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- on-device collate ------------------------------------------------------------------------
+ * datamodule/data_module.py:10-41 (`pad` / `collate_pad`) on the GPU: the utterances of a max-frames bucket lie back to
+ * back in `flat` (sum of lengths rows x d; offsets[B+1] int64 DEVICE prefix sums), the zero-padded (B, Tmax, d) batch and
+ * its int32 lengths are formed on the device; avsr_unpack_padded is the inverse (valid rows only). */
+int avsr_pack_padded(const float *flat, const int64_t *offsets, float *out, int32_t *lengths_out, int B, int Tmax, int d,
+                     float pad_value, void *stream);
+int avsr_unpack_padded(const float *padded, const int64_t *offsets, float *flat, int B, int Tmax, int d, void *stream);
 
 #ifdef __cplusplus
 }
