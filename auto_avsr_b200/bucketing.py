@@ -85,7 +85,10 @@ def assign_to_ranks(batches: Sequence[Sequence[int]], lengths: Sequence[int], wo
         r = min(range(world_size), key=lambda k: (load[k], k))
         out[r].append(i)
         load[r] += padded_frames(batches[i], lengths)
-    return out
+    # the reference order is already sorted by length, so its round robin can beat the greedy bound: keep the better plan
+    ref = [list(range(r, len(batches), world_size)) for r in range(world_size)]
+    ref_load = max(sum(padded_frames(batches[i], lengths) for i in r) for r in ref) if batches else 0
+    return out if max(load) <= ref_load else ref
 
 
 def pack_bucket(flat: torch.Tensor, lengths: Sequence[int], pad_value: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
