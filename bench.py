@@ -385,6 +385,54 @@ def extras(dev, enc, args, peaks):
         log(f"extras: configs[2] fused {ms_f:.3f} ms, module-by-module {ms_m:.3f} ms")
     except Exception as e:          # noqa: BLE001
         out["configs2_features_to_ctc_logprobs"] = {"error": f"{type(e).__name__}: {e}"}
+    # config 1 caller replay (lightning.py:69-72): B = 1, masks None, a new T per utterance -> direct launches
+    try:
+        from auto_avsr_b200.shim import E2EShell, test_step_encoder
+        shell = E2EShell()
+        shell.encoder, shell.proj_encoder = enc, proj
+        Ts = [100, 37, 251, 64, 180, 99, 33, 400, 12, 77, 313, 58, 129, 240, 91, 17, 365, 204, 146, 63]
+        fs = [frontend_features([T], 512, 1000 + T)[0].to(dev) for T in Ts]
+        with torch.no_grad():
+            for f in fs[:3]:
+                test_step_encoder(shell, f)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for f in fs:
+                test_step_encoder(shell, f)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out["config1_eval_path"] = {"what": "ModelModule.test_step replay (proj_encoder -> encoder(x, None)), 20 utterances with 20 "
+                                            "distinct lengths (12..400 frames), B = 1, wall clock incl. host overhead",
+                                    "utterances_per_s": len(Ts) / dt, "frames_per_s": sum(Ts) / dt,
+                                    "ms_per_utterance": dt / len(Ts) * 1e3,
+                                    "engine_stats": dict(enc._engine.stats)}
+        log(f"extras: config-1 replay {dt / len(Ts) * 1e3:.3f} ms / utterance")
+    except Exception as e:          # noqa: BLE001
+        out["config1_eval_path"] = {"error": f"{type(e).__name__}: {e}"}
+    # training step of the encoder alone: forward + backward in train() mode, reference dropout rates
+    try:
+        enc.train()
+        xt = xs.clone().requires_grad_(False)
+        for _ in range(2):
+            enc.zero_grad(set_to_none=True)
+            enc(xt, mask)[0].pow(2).mean().backward()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            enc.zero_grad(set_to_none=True)
+            enc(xt, mask)[0].pow(2).mean().backward()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        enc.zero_grad(set_to_none=True)
+        enc.eval()
+        out["train_step_encoder"] = {"what": "ConformerEncoder.train(): forward + backward of workload S2 (dropout 0.1, batch-stat "
+                                             "BatchNorm), every module's forward and backward in libavsr_b200; correctness-first "
+                                             "slice (fp32 CUDA-core attention backward, unfused module-by-module schedule)",
+                                     "ms_per_step": dt * 1e3, "frames_per_s": sum(lengths) / dt}
+        log(f"extras: train step {dt * 1e3:.1f} ms")
+    except Exception as e:          # noqa: BLE001
+        enc.eval()
+        out["train_step_encoder"] = {"error": f"{type(e).__name__}: {e}"}
     # eager-PyTorch comparator on the same GPU (cuBLAS / ATen), same weights and inputs: the UNMODIFIED reference
     # modules moved to cuda when oracle/_ref was built, else the torch restatement (oracle/conformer_oracle.py)
     try:
