@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libav
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class AvsrError(RuntimeError):
@@ -98,6 +98,9 @@ SIGNATURES = {
     "avsr_prepare_head": (_I, [_CFG, _I, _I, _P, _P, _P, _P, _P, _Z, _I, _P]),
     "avsr_head_workspace_bytes": (_Z, [_CFG, _I, _I, _I, _I]),
     "avsr_features_to_logprobs": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _I, _P]),
+    "avsr_head_plan_workspace_bytes": (_Z, [_CFG, _I, _I, _I, _I]),
+    "avsr_head_plan_create": (_I, [_CFG, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _I, _P, C.POINTER(_P)]),
+    "avsr_head_plan_forward": (_I, [_P, _P, _P, _P]),
     "avsr_proj_encoder": (_I, [_CFG, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
     "avsr_ctc_workspace_bytes": (_Z, [_CFG, _I, _I]),
     "avsr_ctc_logprobs": (_I, [_CFG, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _I, _P]),

@@ -499,6 +499,26 @@ static int ctc_logprobs(const AvsrEncoderConfig& c, const HeadPrep& H, const voi
   return launch_log_softmax_rows(logits, H.npad, logp, odim, argmax, rows, odim, st);
 }
 
+// features (already resident at `feats`) -> enc_out / logp / argmax: the schedule both the direct call and the captured
+// plan run.  `aux` (optional) forks the rel-pos branch like forward_body does.
+static int head_forward_body(const AvsrEncoderConfig& c, const Prepared& P, const HeadPrep& H, const Workspace& W,
+                             const HeadWorkspace& HW, const float* feats, const int32_t* lengths, int B, int T, int idim,
+                             int odim, float* enc_out, float* logp, int32_t* argmax, int precision, cudaStream_t st,
+                             const AuxFork* aux) {
+  const int N = B * T, D = c.d_model;
+  // (1) proj_encoder with the embed scale folded in, straight into the residual stream: x = sqrt(d) * (f Wp^T + bp)
+  const void* fx = feats;
+  if (precision != AVSR_PREC_FP32) { AVSR_TRY(copy_round(feats, HW.fx, (long)N * idim, operand_kind(precision), st)); fx = HW.fx; }
+  AVSR_TRY(run_gemm(precision, EPI_LINEAR, fx, H.proj_ws, N, D, idim, epi_linear(N, D, H.proj_bs, W.x, nullptr, 0.f, 0, 0), st));
+  // (2) the 12 layers
+  AVSR_TRY(forward_body(c, P, W, B, T, lengths, nullptr, precision, st, aux));
+  // (3) after_norm: fp32 features for the caller (attention decoder / beam search) + the operand of ctc_lo in one pass
+  float* feat_out = enc_out ? enc_out : W.x;
+  AVSR_TRY(launch_layernorm_dual(W.x, P.after_w, P.after_b, feat_out, W.xn, N, D, operand_kind(precision), st));
+  // (4) ctc_lo + log_softmax: GEMM with log-sum-exp partials in its epilogue, one finishing pass
+  return ctc_logprobs(c, H, W.xn, N, odim, HW.logits, HW.parts, logp, argmax, precision, st);
+}
+
 }  // namespace avsr
 
 // ====================================================================== C ABI
@@ -509,6 +529,8 @@ struct AvsrPlan {
   Prepared P;
   Workspace W;
   int B, T, precision;
+  float* head_feats = nullptr;     // head plans: staging copy of the features inside the plan's workspace
+  int head_idim = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };
@@ -1007,18 +1029,86 @@ int avsr_features_to_logprobs(const AvsrEncoderConfig* cfg, const void* prepared
   Prepared P = layout_prepared(*cfg, const_cast<void*>(prepared));
   HeadPrep H = layout_head(*cfg, idim, odim, const_cast<void*>(prepared_head));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int N = B * T, D = cfg->d_model;
-  // (1) proj_encoder with the embed scale folded in, straight into the residual stream: x = sqrt(d) * (f Wp^T + bp)
-  const void* fx = feats;
-  if (precision != AVSR_PREC_FP32) { AVSR_TRY(copy_round(feats, HW.fx, (long)N * idim, operand_kind(precision), st)); fx = HW.fx; }
-  AVSR_TRY(run_gemm(precision, EPI_LINEAR, fx, H.proj_ws, N, D, idim, epi_linear(N, D, H.proj_bs, W.x, nullptr, 0.f, 0, 0), st));
-  // (2) the 12 layers
-  AVSR_TRY(forward_body(*cfg, P, W, B, T, lengths, nullptr, precision, st));
-  // (3) after_norm: fp32 features for the caller (attention decoder / beam search) + the operand of ctc_lo in one pass
-  float* feat_out = enc_out ? enc_out : W.x;
-  AVSR_TRY(launch_layernorm_dual(W.x, P.after_w, P.after_b, feat_out, W.xn, N, D, operand_kind(precision), st));
-  // (4) ctc_lo + log_softmax: GEMM with log-sum-exp partials in its epilogue, one finishing pass
-  return ctc_logprobs(*cfg, H, W.xn, N, odim, HW.logits, HW.parts, logp, argmax, precision, st);
+  return head_forward_body(*cfg, P, H, W, HW, feats, lengths, B, T, idim, odim, enc_out, logp, argmax, precision, st, nullptr);
+}
+
+// The same call replayed from a CUDA graph.  The plan bakes in its buffers: `workspace` (>= avsr_head_plan_workspace_bytes:
+// the head workspace + a staging copy of the features + the lengths) and the OUTPUT buffers enc_out / logp / argmax given
+// here -- every avsr_head_plan_forward writes into those same buffers.
+size_t avsr_head_plan_workspace_bytes(const AvsrEncoderConfig* cfg, int B, int T, int idim, int odim) {
+  if (check_cfg(cfg) != AVSR_OK || B <= 0 || T <= 0 || idim <= 0 || odim <= 0) return 0;
+  return layout_head_workspace(*cfg, B, T, idim, odim, nullptr).bytes + align_up((size_t)B * T * idim * sizeof(float), 256) + 256;
+}
+
+int avsr_head_plan_create(const AvsrEncoderConfig* cfg, const void* prepared, const void* prepared_head, int B, int T,
+                          int idim, int odim, float* enc_out, float* logp, int32_t* argmax, void* workspace,
+                          size_t workspace_bytes, int precision, void* stream, AvsrPlan** plan) {
+  AVSR_TRY(check_cfg(cfg));
+  AVSR_REQUIRE(plan && prepared && prepared_head && workspace && (logp || argmax), "NULL argument");
+  AVSR_REQUIRE(B > 0 && T > 0 && idim > 0 && odim > 0, "plan needs B>0, T>0 (got %d, %d)", B, T);
+  AVSR_REQUIRE(valid_precision(precision), "bad precision %d", precision);
+  if (avsr_head_plan_workspace_bytes(cfg, B, T, idim, odim) > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", avsr_head_plan_workspace_bytes(cfg, B, T, idim, odim), workspace_bytes);
+    return AVSR_E_WORKSPACE;
+  }
+  HeadWorkspace HW = layout_head_workspace(*cfg, B, T, idim, odim, workspace);
+  float* feats_static = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(HW.bytes, 256));
+  AvsrPlan* p = new AvsrPlan();
+  p->cfg = *cfg; p->B = B; p->T = T; p->precision = precision;
+  p->W = layout_workspace(*cfg, B, T, HW.enc);
+  p->P = layout_prepared(*cfg, const_cast<void*>(prepared));
+  p->head_feats = feats_static; p->head_idim = idim;
+  const HeadPrep H = layout_head(*cfg, idim, odim, const_cast<void*>(prepared_head));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  fill_lengths_kernel<<<cdiv(B, 128), 128, 0, st>>>(p->W.lengths, nullptr, B, T);
+  g_launches.fetch_add(1);
+  AVSR_CUDA_TRY(cudaMemsetAsync(feats_static, 0, (size_t)B * T * idim * sizeof(float), st));
+  AuxFork aux;
+  if (cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("plan: cannot create the auxiliary stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return AVSR_E_CUDA;
+  }
+  auto drop_aux = [&]() { cudaEventDestroy(aux.fork); cudaEventDestroy(aux.join); cudaStreamDestroy(aux.stream); };
+  auto run_all = [&]() -> int {
+    return head_forward_body(p->cfg, p->P, H, p->W, HW, feats_static, p->W.lengths, B, T, idim, odim, enc_out, logp, argmax,
+                             precision, st, &aux);
+  };
+  int rc = run_all();     // warm-up outside capture (function attributes, lazy module loading)
+  if (rc == AVSR_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaStreamSynchronize(aux.stream) != cudaSuccess)) {
+    set_error("plan warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = AVSR_E_CUDA;
+  }
+  if (rc != AVSR_OK) { drop_aux(); delete p; return rc; }
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); drop_aux(); delete p; return AVSR_E_CUDA; }
+  const uint64_t before = g_launches.load();
+  rc = run_all();
+  g_launches.store(before);
+  e = cudaStreamEndCapture(st, &p->graph);
+  drop_aux();
+  if (rc != AVSR_OK) { if (p->graph) cudaGraphDestroy(p->graph); delete p; return rc; }
+  if (e != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); delete p; return AVSR_E_CUDA; }
+  e = cudaGraphInstantiate(&p->exec, p->graph, 0);
+  if (e != cudaSuccess) {
+    set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    cudaGraphDestroy(p->graph); delete p; return AVSR_E_CUDA;
+  }
+  *plan = p;
+  return AVSR_OK;
+}
+
+int avsr_head_plan_forward(AvsrPlan* p, const float* feats, const int32_t* lengths, void* stream) {
+  AVSR_REQUIRE(p && feats && p->head_feats, "NULL argument / not a head plan");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  fill_lengths_kernel<<<cdiv(p->B, 128), 128, 0, st>>>(p->W.lengths, lengths, p->B, p->T);
+  AVSR_CHECK_LAUNCH();
+  AVSR_CUDA_TRY(cudaMemcpyAsync(p->head_feats, feats, (size_t)p->B * p->T * p->head_idim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AVSR_CUDA_TRY(cudaGraphLaunch(p->exec, st));
+  g_launches.fetch_add(graph_kernel_nodes(p->graph));
+  return AVSR_OK;
 }
 
 int avsr_rel_sinusoid_table(float* pe, int T, int d, void* stream) {

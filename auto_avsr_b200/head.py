@@ -21,6 +21,21 @@ class PreparedHead:
         self.cfg = EncoderConfig(d_model, n_heads, linear_units, num_blocks, cnn_kernel)
         self._buf: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self._plans: Dict[tuple, tuple] = {}          # shape key -> (plan, workspace, enc_out, logp, argmax)
+        self._seen: Dict[tuple, int] = {}
+        self._capture_stream: Dict[int, torch.cuda.Stream] = {}
+
+    def __del__(self):
+        try:
+            for plan, *_ in self._plans.values():
+                lib.avsr_plan_destroy(plan)
+        except Exception:
+            pass
+
+    def drop_plans(self) -> None:
+        for plan, *_ in self._plans.values():
+            lib.avsr_plan_destroy(plan)
+        self._plans.clear()
 
     @staticmethod
     def _fp(*tensors) -> tuple:
@@ -50,6 +65,7 @@ class PreparedHead:
             check(lib.avsr_prepare_head(C.byref(self.cfg), idim, odim, _ptr(pw), _ptr(pb), _ptr(cw), _ptr(cb),
                                         buf.data_ptr(), nbytes, PRECISIONS[precision], _stream_handle(device)))
         self._buf[key] = (fp, buf)
+        self.drop_plans()                       # plans bake the prepared buffers' addresses
         return buf, idim, odim
 
     def workspace(self, tag: str, nbytes: int, device) -> torch.Tensor:
@@ -99,7 +115,9 @@ def features_to_log_probs(proj: torch.nn.Linear, encoder, ctc, feats: torch.Tens
     ``proj`` is E2E.proj_encoder, ``encoder`` the drop-in ConformerEncoder, ``ctc`` E2E.ctc (anything with a ``ctc_lo``
     Linear): the reference's inference path e2e_asr_conformer.py:70-71 + ctc.py:77-84 in ONE library call --
     proj_encoder writes sqrt(d)-scaled rows straight into the residual stream, after_norm emits ctc_lo's operand, the
-    ctc_lo GEMM leaves log-sum-exp partials for a single finishing pass."""
+    ctc_lo GEMM leaves log-sum-exp partials for a single finishing pass.  A (B, T) shape that keeps coming back is replayed
+    from a CUDA graph (``encoder.use_graph`` / ``graph_after``): then the returned tensors belong to the plan and are
+    overwritten by the next call with that shape -- clone them to keep them."""
     from .espnet_dropin.attention import mask_to_lengths
     if encoder.training:
         raise NotImplementedError("features_to_log_probs: inference only (call .eval())")
@@ -117,6 +135,41 @@ def features_to_log_probs(proj: torch.nn.Linear, encoder, ctc, feats: torch.Tens
     if head is None:
         head = encoder._fused_head = PreparedHead(*encoder._cfg)
     hbuf, idim, odim = head.prepare(proj, ctc.ctc_lo, dev, precision)
+    if B and T and encoder.use_graph and not getattr(encoder, "check_saturation", False):
+        # CUDA-graph replay once the shape has been seen `graph_after` times (same policy as the encoder's own plans).
+        # The plan owns its output tensors: the ones returned here are overwritten by the next call with this shape.
+        st = _stream_handle(dev)
+        key = (dev.index or 0, B, T, idim, odim, PRECISIONS[precision], prepared.data_ptr(), hbuf.data_ptr(), st,
+               want_features, want_argmax)
+        hit = head._plans.get(key)
+        if hit is None:
+            seen = head._seen[key] = head._seen.get(key, 0) + 1
+            if seen >= encoder._engine.graph_after:
+                nbytes = int(lib.avsr_head_plan_workspace_bytes(C.byref(head.cfg), B, T, idim, odim))
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                eo = torch.empty(B, T, head.cfg.d_model, dtype=torch.float32, device=dev) if want_features else None
+                lp = torch.empty(B, T, odim, dtype=torch.float32, device=dev)
+                am = torch.empty(B, T, dtype=torch.int32, device=dev) if want_argmax else None
+                idx = dev.index or 0
+                if idx not in head._capture_stream:
+                    head._capture_stream[idx] = torch.cuda.Stream(device=dev)
+                cs = head._capture_stream[idx]
+                cs.wait_stream(torch.cuda.current_stream(dev))
+                plan = C.c_void_p()
+                with torch.cuda.device(dev):
+                    check(lib.avsr_head_plan_create(C.byref(head.cfg), prepared.data_ptr(), hbuf.data_ptr(), B, T, idim, odim,
+                                                    _ptr(eo), lp.data_ptr(), _ptr(am), ws.data_ptr(), nbytes,
+                                                    PRECISIONS[precision], cs.cuda_stream, C.byref(plan)))
+                cs.synchronize()
+                hit = head._plans[key] = (plan, ws, eo, lp, am)
+                while len(head._plans) > encoder._engine.MAX_PLANS:
+                    old = head._plans.pop(next(iter(head._plans)))
+                    lib.avsr_plan_destroy(old[0])
+        if hit is not None:
+            plan, _ws, eo, lp, am = hit
+            with torch.cuda.device(dev):
+                check(lib.avsr_head_plan_forward(plan, feats.data_ptr(), _ptr(lengths), st))
+            return eo, lp, (None if am is None else am.long())
     enc_out = torch.empty(B, T, head.cfg.d_model, dtype=torch.float32, device=dev) if want_features else None
     logp = torch.empty(B, T, odim, dtype=torch.float32, device=dev)
     best = torch.empty(B, T, dtype=torch.int32, device=dev) if want_argmax else None

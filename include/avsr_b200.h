@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 7
+#define AVSR_ABI_VERSION 8
 
 enum {
   AVSR_OK = 0,
@@ -208,6 +208,16 @@ int avsr_features_to_logprobs(const AvsrEncoderConfig *cfg, const void *prepared
                               const float *feats, const int32_t *lengths, int B, int T, int idim, int odim,
                               float *enc_out, float *logp, int32_t *argmax, void *workspace,
                               size_t workspace_bytes, int precision, void *stream);
+
+/* avsr_features_to_logprobs replayed from a CUDA graph (fixed B, T).  The plan bakes in `workspace`
+ * (>= avsr_head_plan_workspace_bytes) AND the output buffers given at creation: every avsr_head_plan_forward copies the
+ * features into the plan's staging buffer, replays the graph and leaves its results in those same enc_out / logp /
+ * argmax buffers (enc_out / argmax may be NULL).  Destroy with avsr_plan_destroy. */
+size_t avsr_head_plan_workspace_bytes(const AvsrEncoderConfig *cfg, int B, int T, int idim, int odim);
+int avsr_head_plan_create(const AvsrEncoderConfig *cfg, const void *prepared, const void *prepared_head, int B, int T,
+                          int idim, int odim, float *enc_out, float *logp, int32_t *argmax, void *workspace,
+                          size_t workspace_bytes, int precision, void *stream, AvsrPlan **plan);
+int avsr_head_plan_forward(AvsrPlan *plan, const float *feats, const int32_t *lengths, void *stream);
 
 /* The two projections on their own, on the prepared weights (what the ProjEncoder / CTC drop-in modules call when the
  * reference's E2E.forward drives them one by one): y = feats Wp^T + bp (rows, d_model) fp32, workspace >= rows*idim*4;

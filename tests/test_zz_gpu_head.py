@@ -139,6 +139,10 @@ with torch.no_grad():
     hs2, logp2, _ = features_to_log_probs(proj, enc, ctc, c["feats"].to(dev), mask, want_features=False)
 z = c["z"]
 assert hs2 is None and torch.equal(logp, logp2)
+keep = logp.clone()
+for _ in range(3):                                    # graph_after = 1 in build(): these replay the captured plan
+    hs3, logp3, best3 = features_to_log_probs(proj, enc, ctc, c["feats"].to(dev), mask, want_argmax=True)
+assert torch.equal(logp3, keep) and torch.equal(hs3, hs) and torch.equal(best3, best)
 mx, rms = err_stats(hs.cpu(), torch.from_numpy(z["enc_f64"]))
 record("fused_enc", ({name!r}, {prec!r}), [mx, rms], list(TOL[{prec!r}]))
 assert mx < TOL[{prec!r}][0] and rms < TOL[{prec!r}][1], ("enc", mx, rms)
