@@ -4,7 +4,7 @@
 // (transformer/attention.py:174-189 + :59-82 of the reference).
 //
 // Why this shape (r02 launch timeline, profiles/r02_timeline_S2_base.txt): the round-1 kernel (128-key tiles, one CTA
-// per SM, attention_f16_v1.cu) is a chain of dependent latencies -- S/G MMA -> TMEM load -> skew -> max -> exp -> P ->
+// per SM; deleted after the r02 A/B: 29.3 vs 21.7 us per launch in situ) is a chain of dependent latencies -- S/G MMA -> TMEM load -> skew -> max -> exp -> P ->
 // P.V MMA -> O load -- with nothing to overlap it, and at T = 400 its 192 CTAs need two waves on 148 SMs, the second
 // (16 valid query rows per CTA) as long as the first: 28 us per launch for 3 us of instruction issue.  This version is
 // built so that TWO CTAs share an SM (one wave of 296 slots; one CTA's latencies hide under the other's work):
@@ -339,9 +339,6 @@ int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __
                   const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st) {
   AVSR_REQUIRE(Rp >= 2 * T - 1, "attention_f16: bad Rp=%d for T=%d", Rp, T);
   if (B <= 0 || T <= 0) return AVSR_OK;
-  // AVSR_B200_ATTN=v1: the round-1 kernel (128-key tiles, one CTA per SM), kept for the A/B of the r02 rewrite
-  static const bool v1 = [] { const char* e = getenv("AVSR_B200_ATTN"); return e && e[0] == 'v' && e[1] == '1'; }();
-  if (v1) return attention_f16_v1(qu, qv, kk, vv, pos, lengths, ctx, B, T, H, Rp, st);
   CUtensorMap tmQu, tmQv, tmK, tmV, tmP, tmCtx;
   const uint64_t rows = (uint64_t)B * H * T;
   const uint64_t D = (uint64_t)H * kHeadDim;

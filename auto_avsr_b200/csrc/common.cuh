@@ -398,8 +398,5 @@ int attention_tc(const float* qu, const float* qv, const float* kk, const float*
 // fp16 operands (attention_f16.cu): qu, qv, kk, vv all (B,H,T,64) __half (V in its natural layout); ctx __half
 int attention_f16(const __half* qu, const __half* qv, const __half* kk, const __half* vv, const __half* pos,
                   const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st);
-// the round-1 kernel (attention_f16_v1.cu: 128-key tiles, one CTA per SM), AVSR_B200_ATTN=v1
-int attention_f16_v1(const __half* qu, const __half* qv, const __half* kk, const __half* vv, const __half* pos,
-                     const int32_t* lengths, __half* ctx, int B, int T, int H, int Rp, cudaStream_t st);
 
 }  // namespace avsr

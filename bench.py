@@ -377,7 +377,7 @@ def extras(dev, enc, args, peaks):
             ms_m = e0.elapsed_time(e1) / 20
         out["configs2_features_to_ctc_logprobs"] = {
             "what": "BASELINE.json configs[2] (ASR Conformer-base encoder fwd + CTC head): synthetic (4, 400, 512) front-end "
-                    "features -> proj_encoder -> 12-layer encoder -> ctc_lo (5049) + log_softmax; direct launches (no graph)",
+                    "features -> proj_encoder -> 12-layer encoder -> ctc_lo (5049) + log_softmax; both paths replay CUDA graphs",
             "fused_call": {"frames_per_s": sum(lengths) / (ms_f * 1e-3), "ms_per_step": ms_f,
                            "api": "auto_avsr_b200.head.features_to_log_probs -> avsr_features_to_logprobs"},
             "module_by_module": {"frames_per_s": sum(lengths) / (ms_m * 1e-3), "ms_per_step": ms_m,
