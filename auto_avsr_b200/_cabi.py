@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libav
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class AvsrError(RuntimeError):
@@ -88,8 +88,11 @@ SIGNATURES = {
     "avsr_relu_bwd": (_I, [_P, _P, _P, C.c_long, _P]),
     "avsr_glu_fwd": (_I, [_P, _P, C.c_long, _I, _P]),
     "avsr_glu_bwd": (_I, [_P, _P, _P, C.c_long, _I, _P]),
-    "avsr_dwconv_bn_silu_train_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
-    "avsr_dwconv_bn_silu_train_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "avsr_dwconv_raw": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "avsr_chan_sums": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "avsr_bn_silu_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "avsr_bn_silu_bwd_dx": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _P]),
+    "avsr_dwconv_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "avsr_relpos_attention_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "avsr_relpos_attention_bwd": (_I, [_P] * 14 + [_I, _I, _I, _P, _Z, _P]),
     "avsr_pack_padded": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P]),

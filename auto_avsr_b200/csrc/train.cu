@@ -168,26 +168,6 @@ __global__ void __launch_bounds__(256) chan_stats_partial_kernel(const float* __
     part[((long)blockIdx.x * 2 + 1) * C + c] = q;
   }
 }
-// mean / invstd of the batch (biased variance, like F.batch_norm in training) + running-statistics update
-// (momentum m: running = (1-m) running + m batch, variance UNBIASED there) -- torch.nn.BatchNorm1d semantics
-__global__ void bn_stats_finish_kernel(const float* __restrict__ part, int nblk, int rows, int C, float eps, float momentum,
-                                       float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                       float* running_mean, float* running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) { s += part[((long)b * 2) * C + c]; q += part[((long)b * 2 + 1) * C + c]; }
-  const double mean = s / rows;
-  double var = q / rows - mean * mean;
-  if (var < 0.0) var = 0.0;
-  save_mean[c] = (float)mean;
-  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    const double unb = rows > 1 ? var * rows / (rows - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
-    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
-  }
-}
 // y = silu((v - mean) * invstd * gamma + beta)
 __global__ void bn_silu_fwd_kernel(const float4* __restrict__ v, const float* __restrict__ mean, const float* __restrict__ invstd,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float4* __restrict__ y,
@@ -379,80 +359,84 @@ int avsr_glu_bwd(const float* in, const float* dy, float* din, long rows, int C,
   return AVSR_OK;
 }
 
-int avsr_dwconv_bn_silu_train_fwd(const float* x, const float* w, const float* b, const float* bn_w, const float* bn_b,
-                                  float* running_mean, float* running_var, float momentum, float eps, float* y,
-                                  float* conv_out, float* save_mean, float* save_invstd, int B, int T, int C, int K,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
-  AVSR_REQUIRE(x && w && b && bn_w && bn_b && y && conv_out && save_mean && save_invstd && workspace, "NULL argument");
-  AVSR_REQUIRE(C > 0 && C % 4 == 0 && K >= 1 && K % 2 == 1, "dwconv train: bad C=%d K=%d", C, K);
-  if (B <= 0 || T <= 0) return AVSR_OK;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rows = B * T;
-  const int rpc = cdiv(rows, kRedBlocks), nb = cdiv(rows, rpc);
-  const size_t need = ((size_t)(K + 2) * C + (size_t)nb * 2 * C) * sizeof(float);
-  if (need > workspace_bytes) { set_error("dwconv train fwd workspace too small: need %zu, got %zu", need, workspace_bytes); return AVSR_E_WORKSPACE; }
-  float* wt = reinterpret_cast<float*>(workspace);
-  float *ones = wt + (size_t)K * C, *part = ones + 2 * (size_t)C;
-  dw_taps_kernel<<<cdiv(K * C, 256), 256, 0, st>>>(w, wt, C, K, 0);
-  AVSR_CHECK_LAUNCH();
-  fill_kernel<<<cdiv(C, 256), 256, 0, st>>>(ones, C, 1.0f);
-  AVSR_CHECK_LAUNCH();
-  // conv + bias, raw (no BN fold, no SiLU): scale = 1, shift = conv bias
-  AVSR_TRY(launch_dwconv_bn_silu(x, wt, ones, b, conv_out, B, T, C, K, /*out_kind=*/-1, st));
-  chan_stats_partial_kernel<<<nb, 256, 0, st>>>(conv_out, part, rows, C, rpc);
-  AVSR_CHECK_LAUNCH();
-  bn_stats_finish_kernel<<<cdiv(C, 128), 128, 0, st>>>(part, nb, rows, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
-  AVSR_CHECK_LAUNCH();
-  bn_silu_fwd_kernel<<<grid_for((long)rows * C / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(conv_out), save_mean, save_invstd,
-                                                                   bn_w, bn_b, reinterpret_cast<float4*>(y), (long)rows * C / 4, C / 4);
-  AVSR_CHECK_LAUNCH();
-  return AVSR_OK;
-}
+// ---- depthwise conv + BatchNorm (training) + SiLU, in the pieces a (Sync)BatchNorm needs: the per-channel sums leave the
+// library between the pieces so that the host can all-reduce them over the ranks (torch.nn.SyncBatchNorm semantics,
+// train.py:31) before the statistics are finalised.
 
-int avsr_dwconv_bn_silu_train_bwd(const float* x, const float* w, const float* conv_out, const float* save_mean,
-                                  const float* save_invstd, const float* bn_w, const float* bn_b, const float* dy, float* dx,
-                                  float* dw, float* db, float* dbn_w, float* dbn_b, int B, int T, int C, int K,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
-  AVSR_REQUIRE(x && w && conv_out && save_mean && save_invstd && bn_w && bn_b && dy && dx && dw && db && dbn_w && dbn_b && workspace,
-               "NULL argument");
-  AVSR_REQUIRE(C > 0 && C % 4 == 0 && K >= 1 && K % 2 == 1, "dwconv train: bad C=%d K=%d", C, K);
+// y = depthwise_conv(x) + b (raw fp32; flip != 0: taps reversed along k and b may be NULL -- the input gradient)
+int avsr_dwconv_raw(const float* x, const float* w, const float* b, float* y, int B, int T, int C, int K, int flip,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  AVSR_REQUIRE(x && w && y && workspace, "NULL argument");
+  AVSR_REQUIRE(C > 0 && C % 4 == 0 && K >= 1 && K % 2 == 1, "dwconv: bad C=%d K=%d", C, K);
   if (B <= 0 || T <= 0) return AVSR_OK;
+  if ((size_t)(K + 2) * C * sizeof(float) > workspace_bytes) { set_error("dwconv_raw workspace too small"); return AVSR_E_WORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rows = B * T;
-  const int rpc = cdiv(rows, kRedBlocks), nb = cdiv(rows, rpc);
-  int cpu_ = cdiv(kRedBlocks, B);                 // CTAs per utterance of the tap-gradient reduction
-  if (cpu_ < 1) cpu_ = 1;
-  const int fpc = cdiv(T, cpu_);
-  cpu_ = cdiv(T, fpc);
-  const int nbw = B * cpu_;
-  const size_t need = ((size_t)(K + 2) * C + (size_t)nb * 2 * C + (size_t)nbw * (K + 1) * C + (size_t)rows * C) * sizeof(float);
-  if (need > workspace_bytes) { set_error("dwconv train bwd workspace too small: need %zu, got %zu", need, workspace_bytes); return AVSR_E_WORKSPACE; }
   float* wt = reinterpret_cast<float*>(workspace);
-  float *ones = wt + (size_t)K * C, *zeros = ones + C, *part = zeros + C;
-  float* partw = part + (size_t)nb * 2 * C;
-  float* dconv = partw + (size_t)nbw * (K + 1) * C;
-  // (1) BatchNorm + SiLU backward: channel sums of ds and ds * x_hat, then dconv
-  bn_bwd_partial_kernel<<<nb, 256, 0, st>>>(conv_out, dy, save_mean, save_invstd, bn_w, bn_b, part, rows, C, rpc);
-  AVSR_CHECK_LAUNCH();
-  // part[b][0] = sum ds (dbeta), part[b][1] = sum ds * x_hat (dgamma): reduce into zeros|... use dbn_b / dbn_w directly
-  {
-    // reduce with width 2*C into a temporary laid out [dbeta | dgamma] inside `partw` (free until step 3)
-    reduce_partials_kernel<<<cdiv(2 * C, 256), 256, 0, st>>>(part, partw, nb, 2 * C);
-    AVSR_CHECK_LAUNCH();
-    AVSR_CUDA_TRY(cudaMemcpyAsync(dbn_b, partw, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    AVSR_CUDA_TRY(cudaMemcpyAsync(dbn_w, partw + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
-  bn_bwd_dx_kernel<<<grid_for((long)rows * C), 256, 0, st>>>(conv_out, dy, save_mean, save_invstd, bn_w, bn_b, dbn_w, dbn_b, dconv,
-                                                             (long)rows * C, C, 1.0f / (float)rows);
-  AVSR_CHECK_LAUNCH();
-  // (2) input gradient: depthwise correlation of dconv with the flipped taps (same kernel as the forward, raw output)
-  dw_taps_kernel<<<cdiv(K * C, 256), 256, 0, st>>>(w, wt, C, K, 1);
+  float *ones = wt + (size_t)K * C, *zeros = ones + C;
+  dw_taps_kernel<<<cdiv(K * C, 256), 256, 0, st>>>(w, wt, C, K, flip);
   AVSR_CHECK_LAUNCH();
   fill_kernel<<<cdiv(C, 256), 256, 0, st>>>(ones, C, 1.0f);
   AVSR_CHECK_LAUNCH();
   AVSR_CUDA_TRY(cudaMemsetAsync(zeros, 0, C * sizeof(float), st));
-  AVSR_TRY(launch_dwconv_bn_silu(dconv, wt, ones, zeros, dx, B, T, C, K, /*out_kind=*/-1, st));
-  // (3) tap / bias gradients
+  return launch_dwconv_bn_silu(x, wt, ones, b ? b : zeros, y, B, T, C, K, /*out_kind=*/-1, st);
+}
+
+// sums (2, C): dy == NULL -> [sum v, sum v^2] over the rows; else the BatchNorm+SiLU backward sums [sum ds, sum ds*x_hat]
+// with h = x_hat * gamma + beta, ds = dL/dh of y = silu(h)
+int avsr_chan_sums(const float* v, const float* dy, const float* mean, const float* invstd, const float* gamma,
+                   const float* beta, float* sums, int rows, int C, void* workspace, size_t workspace_bytes, void* stream) {
+  AVSR_REQUIRE(v && sums && workspace && C > 0, "NULL / bad argument");
+  AVSR_REQUIRE(!dy || (mean && invstd && gamma && beta), "chan_sums: the backward sums need mean / invstd / gamma / beta");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (rows <= 0) { AVSR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st)); return AVSR_OK; }
+  const int rpc = cdiv(rows, kRedBlocks), nb = cdiv(rows, rpc);
+  if ((size_t)nb * 2 * C * sizeof(float) > workspace_bytes) { set_error("chan_sums workspace too small"); return AVSR_E_WORKSPACE; }
+  float* part = reinterpret_cast<float*>(workspace);
+  if (dy) bn_bwd_partial_kernel<<<nb, 256, 0, st>>>(v, dy, mean, invstd, gamma, beta, part, rows, C, rpc);
+  else chan_stats_partial_kernel<<<nb, 256, 0, st>>>(v, part, rows, C, rpc);
+  AVSR_CHECK_LAUNCH();
+  reduce_partials_kernel<<<cdiv(2 * C, 256), 256, 0, st>>>(part, sums, nb, 2 * C);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// y = silu((v - mean) * invstd * gamma + beta)
+int avsr_bn_silu_fwd(const float* v, const float* mean, const float* invstd, const float* gamma, const float* beta, float* y,
+                     int rows, int C, void* stream) {
+  AVSR_REQUIRE(v && mean && invstd && gamma && beta && y && C > 0 && C % 4 == 0, "NULL / bad argument");
+  if (rows <= 0) return AVSR_OK;
+  bn_silu_fwd_kernel<<<grid_for((long)rows * C / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(v), mean, invstd, gamma, beta, reinterpret_cast<float4*>(y), (long)rows * C / 4, C / 4);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// dv = gamma * invstd * (ds - inv_count * (sum_ds + x_hat * sum_dsx)): sum_ds / sum_dsx (C) and inv_count are GLOBAL
+// (over all ranks' rows under SyncBatchNorm)
+int avsr_bn_silu_bwd_dx(const float* v, const float* dy, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, const float* sum_ds, const float* sum_dsx, float inv_count, float* dv, int rows,
+                        int C, void* stream) {
+  AVSR_REQUIRE(v && dy && mean && invstd && gamma && beta && sum_ds && sum_dsx && dv && C > 0, "NULL / bad argument");
+  if (rows <= 0) return AVSR_OK;
+  bn_bwd_dx_kernel<<<grid_for((long)rows * C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      v, dy, mean, invstd, gamma, beta, sum_dsx, sum_ds, dv, (long)rows * C, C, inv_count);
+  AVSR_CHECK_LAUNCH();
+  return AVSR_OK;
+}
+
+// dw (C,1,K), db (C) of the depthwise conv from its input x and its output gradient dconv
+int avsr_dwconv_wgrad(const float* x, const float* dconv, float* dw, float* db, int B, int T, int C, int K, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  AVSR_REQUIRE(x && dconv && dw && db && workspace, "NULL argument");
+  if (B <= 0 || T <= 0) return AVSR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int cpu_ = cdiv(kRedBlocks, B);
+  if (cpu_ < 1) cpu_ = 1;
+  const int fpc = cdiv(T, cpu_);
+  cpu_ = cdiv(T, fpc);
+  const int nbw = B * cpu_;
+  if ((size_t)nbw * (K + 1) * C * sizeof(float) > workspace_bytes) { set_error("dwconv_wgrad workspace too small"); return AVSR_E_WORKSPACE; }
+  float* partw = reinterpret_cast<float*>(workspace);
   dwconv_wgrad_partial_kernel<<<nbw, 256, 0, st>>>(x, dconv, partw, B, T, C, K, fpc, cpu_);
   AVSR_CHECK_LAUNCH();
   dwconv_wgrad_finish_kernel<<<cdiv((K + 1) * C, 256), 256, 0, st>>>(partw, dw, db, nbw, C, K);

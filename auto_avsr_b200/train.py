@@ -7,7 +7,8 @@ and the residual adds; no module falls back to PyTorch arithmetic for its own fo
 
 The rel-pos attention core has a (correctness-first, fp32 CUDA-core) backward too, so a whole ``EncoderLayer`` /
 ``ConformerEncoder`` runs ``train()``: the reference's layer schedule with its dropouts (conformer_encoder.py:96-170).
-Not built: SyncBatchNorm's cross-rank statistics, dropout on attention probabilities (the reference trains with 0.0).
+SyncBatchNorm (train.py:31) is honoured: the per-channel sums are all-reduced between the library's passes.
+Not built: dropout on attention probabilities (the reference trains with 0.0).
 
 Backward GEMMs run with TF32 operands (fp32 range: gradients do not fit fp16's) unless ``precision="fp32"``."""
 from __future__ import annotations
@@ -169,25 +170,65 @@ class GluFn(torch.autograd.Function):
         return dx
 
 
+def _chan_sums(v, dy=None, mean=None, invstd=None, gamma=None, beta=None):
+    """(2, C): [sum v, sum v^2] over all rows, or (dy given) the BatchNorm+SiLU backward sums [sum ds, sum ds * x_hat]."""
+    Cc = v.size(-1)
+    rows = v.numel() // Cc
+    out = torch.empty(2, Cc, dtype=torch.float32, device=v.device)
+    ws = _workspace(v.device, 148 * 2 * Cc * 4 + 1024)
+    with torch.cuda.device(v.device):
+        check(lib.avsr_chan_sums(v.data_ptr(), _ptr(dy), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), out.data_ptr(),
+                                 rows, Cc, ws.data_ptr(), ws.numel(), _stream_handle(v.device)))
+    return out
+
+
+def _dwconv_raw(x, w, b, flip: bool):
+    B, T, Cc = x.shape
+    K = w.size(-1)
+    y = torch.empty_like(x)
+    ws = _workspace(x.device, (K + 2) * Cc * 4 + 1024)
+    with torch.cuda.device(x.device):
+        check(lib.avsr_dwconv_raw(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), B, T, Cc, K, int(flip), ws.data_ptr(),
+                                  ws.numel(), _stream_handle(x.device)))
+    return y
+
+
 class DwConvBnSiluFn(torch.autograd.Function):
-    """depthwise Conv1d + BatchNorm1d (training: batch statistics over all B*T frames, running stats updated in place)
-    + SiLU on (B, T, C) (conformer_encoder.py:33-34)."""
+    """depthwise Conv1d + BatchNorm1d / SyncBatchNorm (training: batch statistics over all B*T frames -- of ALL ranks of
+    ``group`` when given --, running stats updated in place) + SiLU on (B, T, C) (conformer_encoder.py:33-34).
+
+    The heavy passes (conv, per-channel sums, normalise + SiLU, their backward, tap gradients) run in libavsr_b200; the
+    C-length statistics vectors are finalised here between them, which is where SyncBatchNorm's all-reduce goes
+    (one packed [sum, sum^2, count] message forward, [sum ds, sum ds*x_hat] backward: torch/_functions.py:49-159)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, bn_w, bn_b, running_mean, running_var, momentum: float, eps: float):
+    def forward(ctx, x, w, b, bn_w, bn_b, running_mean, running_var, momentum: float, eps: float, group):
         require_cuda(x, "conv module input")
         x, w, b, bn_w, bn_b = _c(x), _c(w), _c(b), _c(bn_w), _c(bn_b)
         B, T, Cc = x.shape
-        K = w.size(-1)
-        y, conv = torch.empty_like(x), torch.empty_like(x)
-        mean, invstd = torch.empty(Cc, device=x.device), torch.empty(Cc, device=x.device)
-        ws = _workspace(x.device, int(lib.avsr_train_workspace_bytes(B * T, Cc, K)))
+        conv = _dwconv_raw(x, w, b, False)
+        sums = _chan_sums(conv)
+        n = float(B * T)
+        if group is not None:
+            packed = torch.cat([sums.reshape(-1), torch.full((1,), n, dtype=torch.float32, device=x.device)])
+            torch.distributed.all_reduce(packed, group=group)
+            sums, n = packed[:-1].reshape(2, Cc), float(packed[-1].item())      # global row count (one host sync)
+        sums64 = sums.double()
+        mean = sums64[0] / n
+        var = (sums64[1] / n - mean * mean).clamp_min_(0.0)
+        invstd = torch.rsqrt(var + eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                unbiased = var * (n / max(n - 1.0, 1.0))
+                running_mean.mul_(1.0 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1.0 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
+        mean, invstd = mean.float().contiguous(), invstd.float().contiguous()
+        y = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            check(lib.avsr_dwconv_bn_silu_train_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), bn_w.data_ptr(), bn_b.data_ptr(),
-                                                    _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
-                                                    y.data_ptr(), conv.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                                    B, T, Cc, K, ws.data_ptr(), ws.numel(), _stream_handle(x.device)))
+            check(lib.avsr_bn_silu_fwd(conv.data_ptr(), mean.data_ptr(), invstd.data_ptr(), bn_w.data_ptr(), bn_b.data_ptr(),
+                                       y.data_ptr(), B * T, Cc, _stream_handle(x.device)))
         ctx.save_for_backward(x, w, conv, mean, invstd, bn_w, bn_b)
+        ctx.group, ctx.inv_count = group, 1.0 / n
         ctx.mark_non_differentiable(*[t for t in (running_mean, running_var) if t is not None])
         return y
 
@@ -197,15 +238,24 @@ class DwConvBnSiluFn(torch.autograd.Function):
         dy = _c(dy)
         B, T, Cc = x.shape
         K = w.size(-1)
-        dx, dw = torch.empty_like(x), torch.empty_like(w)
-        db, dg, dbt = (torch.empty(Cc, device=x.device) for _ in range(3))
+        local = _chan_sums(conv, dy, mean, invstd, bn_w, bn_b)            # [sum ds, sum ds * x_hat] of THIS rank
+        dbt, dg = local[0].clone(), local[1].clone()                       # d beta, d gamma: local sums (DDP averages them)
+        glob = local
+        if ctx.group is not None:
+            glob = local.clone()
+            torch.distributed.all_reduce(glob, group=ctx.group)
+        dconv = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib.avsr_bn_silu_bwd_dx(conv.data_ptr(), dy.data_ptr(), mean.data_ptr(), invstd.data_ptr(), bn_w.data_ptr(),
+                                          bn_b.data_ptr(), glob[0].contiguous().data_ptr(), glob[1].contiguous().data_ptr(),
+                                          float(ctx.inv_count), dconv.data_ptr(), B * T, Cc, _stream_handle(x.device)))
+        dx = _dwconv_raw(dconv, w, None, True)                             # correlation with the flipped taps
+        dw, db = torch.empty_like(w), torch.empty(Cc, device=x.device)
         ws = _workspace(x.device, int(lib.avsr_train_workspace_bytes(B * T, Cc, K)))
         with torch.cuda.device(x.device):
-            check(lib.avsr_dwconv_bn_silu_train_bwd(x.data_ptr(), w.data_ptr(), conv.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                                    bn_w.data_ptr(), bn_b.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(),
-                                                    db.data_ptr(), dg.data_ptr(), dbt.data_ptr(), B, T, Cc, K, ws.data_ptr(),
-                                                    ws.numel(), _stream_handle(x.device)))
-        return dx, dw, db, dg, dbt, None, None, None, None
+            check(lib.avsr_dwconv_wgrad(x.data_ptr(), dconv.data_ptr(), dw.data_ptr(), db.data_ptr(), B, T, Cc, K, ws.data_ptr(),
+                                        ws.numel(), _stream_handle(x.device)))
+        return dx, dw, db, dg, dbt, None, None, None, None, None
 
 
 class AttentionCoreFn(torch.autograd.Function):
@@ -254,16 +304,22 @@ def conv_module_train(m, x, precision: str):
     + SiLU -> pointwise_cov2.  ``m.norm`` stays a real BatchNorm1d: its running statistics and num_batches_tracked are
     updated like torch's (momentum None = cumulative average is not supported here)."""
     bn = m.norm
-    if type(bn) is not torch.nn.BatchNorm1d:
-        raise NotImplementedError(f"conv_module.norm is {type(bn).__name__}: only torch.nn.BatchNorm1d runs on the B200 "
-                                  "training slice (SyncBatchNorm's cross-rank statistics are a later slice)")
+    group = None
+    if isinstance(bn, torch.nn.SyncBatchNorm):        # what Lightning's sync_batchnorm=True (train.py:31) turns `norm` into
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+            if dist.get_world_size(group) == 1:
+                group = None
+    elif type(bn) is not torch.nn.BatchNorm1d:
+        raise NotImplementedError(f"conv_module.norm is {type(bn).__name__}: BatchNorm1d / SyncBatchNorm only")
     if bn.momentum is None:
         raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative moving average) is not supported")
     h = LinearFn.apply(x, m.pointwise_cov1.weight, m.pointwise_cov1.bias, False, precision)
     g = GluFn.apply(h)
     track = bn.track_running_stats and bn.running_mean is not None
     y = DwConvBnSiluFn.apply(g, m.depthwise_conv.weight, m.depthwise_conv.bias, bn.weight, bn.bias,
-                             bn.running_mean if track else None, bn.running_var if track else None, bn.momentum, bn.eps)
+                             bn.running_mean if track else None, bn.running_var if track else None, bn.momentum, bn.eps, group)
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return LinearFn.apply(y, m.pointwise_cov2.weight, m.pointwise_cov2.bias, False, precision)

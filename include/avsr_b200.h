@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 8
+#define AVSR_ABI_VERSION 9
 
 enum {
   AVSR_OK = 0,
@@ -248,19 +248,25 @@ int avsr_relu_bwd(const float *y, const float *dy, float *dx, long n, void *stre
 /* F.glu over channels (conformer_encoder.py:32): in (rows, 2C) -> y (rows, C); and its backward din (rows, 2C) */
 int avsr_glu_fwd(const float *in, float *y, long rows, int C, void *stream);
 int avsr_glu_bwd(const float *in, const float *dy, float *din, long rows, int C, void *stream);
-/* depthwise Conv1d(C,C,K,groups=C)+bias -> BatchNorm1d in TRAINING mode (batch statistics over ALL B*T frames incl.
- * padding, biased variance for the normalisation, running_mean / running_var (may be NULL) updated with `momentum` and
- * the unbiased variance, eps as given) -> SiLU (conformer_encoder.py:33-34).  Saves conv_out (B,T,C), save_mean (C),
- * save_invstd (C) for the backward, which returns dx and the gradients of the conv taps (C,1,K), conv bias, BN weight
- * and BN bias. */
-int avsr_dwconv_bn_silu_train_fwd(const float *x, const float *w, const float *b, const float *bn_w, const float *bn_b,
-                                  float *running_mean, float *running_var, float momentum, float eps, float *y,
-                                  float *conv_out, float *save_mean, float *save_invstd, int B, int T, int C, int K,
-                                  void *workspace, size_t workspace_bytes, void *stream);
-int avsr_dwconv_bn_silu_train_bwd(const float *x, const float *w, const float *conv_out, const float *save_mean,
-                                  const float *save_invstd, const float *bn_w, const float *bn_b, const float *dy,
-                                  float *dx, float *dw, float *db, float *dbn_w, float *dbn_b, int B, int T, int C,
-                                  int K, void *workspace, size_t workspace_bytes, void *stream);
+/* depthwise Conv1d(C,C,K,groups=C) -> BatchNorm1d in TRAINING mode -> SiLU (conformer_encoder.py:33-34) in the pieces a
+ * (Sync)BatchNorm needs: the per-channel sums leave the library so that the host can all-reduce them over the ranks
+ * (train.py:31 sync_batchnorm=True) before it finalises mean / invstd / the running statistics.
+ *   avsr_dwconv_raw      y = conv(x) + b, raw fp32 (flip != 0: taps reversed, b may be NULL = the input gradient)
+ *   avsr_chan_sums       sums (2,C): [sum v, sum v^2] (dy NULL) or the backward sums [sum ds, sum ds*x_hat]
+ *   avsr_bn_silu_fwd     y = silu((v - mean) * invstd * gamma + beta)
+ *   avsr_bn_silu_bwd_dx  dv from dy with the GLOBAL sums and 1 / (global row count)
+ *   avsr_dwconv_wgrad    dw (C,1,K), db (C) */
+int avsr_dwconv_raw(const float *x, const float *w, const float *b, float *y, int B, int T, int C, int K, int flip,
+                    void *workspace, size_t workspace_bytes, void *stream);
+int avsr_chan_sums(const float *v, const float *dy, const float *mean, const float *invstd, const float *gamma,
+                   const float *beta, float *sums, int rows, int C, void *workspace, size_t workspace_bytes, void *stream);
+int avsr_bn_silu_fwd(const float *v, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                     float *y, int rows, int C, void *stream);
+int avsr_bn_silu_bwd_dx(const float *v, const float *dy, const float *mean, const float *invstd, const float *gamma,
+                        const float *beta, const float *sum_ds, const float *sum_dsx, float inv_count, float *dv, int rows,
+                        int C, void *stream);
+int avsr_dwconv_wgrad(const float *x, const float *dconv, float *dw, float *db, int B, int T, int C, int K,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* Backward of the rel-pos attention core (avsr_relpos_attention; transformer/attention.py:174-189 + :59-82), fp32:
  * from q, k, v (B,T,H*64: the projected tensors, biases included), p (2T-1, H*64), pos_bias_u / v (H,64), lengths, the

@@ -27,12 +27,35 @@ def main():
     model = ConformerEncoder(**kw).to(dev).train()
     replica = ConformerEncoder(**kw).to(dev).train()
     replica.load_state_dict(model.state_dict())
+    sync_bn = os.environ.get("AVSR_DDP_SYNCBN", "0") == "1"
+    if sync_bn:     # what Lightning's sync_batchnorm=True does (train.py:31): conv_module.norm -> torch.nn.SyncBatchNorm
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
     g = torch.Generator().manual_seed(100 + rank)
     lengths = [100, 80 - 10 * rank, 64, 33]
     x = torch.randn(4, 100, 768, generator=g).to(dev)
     mask = (torch.arange(100, device=dev)[None, :] < torch.tensor(lengths, device=dev)[:, None]).unsqueeze(1)
     ddp(x, mask)[0].pow(2).mean().backward()
+    if sync_bn:
+        # reference for SyncBatchNorm: ONE process holding both ranks' buckets in one batch sees the same statistics;
+        # every rank rebuilds that: gather the inputs, run the un-wrapped BatchNorm1d replica on the concatenated batch
+        # with the global-mean loss, and compare its gradients with DDP's (mean over ranks of the per-rank losses)
+        xs_all = [torch.empty_like(x) for _ in range(world)]
+        ms_all = [torch.empty_like(mask) for _ in range(world)]
+        dist.all_gather(xs_all, x)
+        dist.all_gather(ms_all, mask)
+        out = replica(torch.cat(xs_all), torch.cat(ms_all))[0]
+        (out.pow(2).mean()).backward()
+        worst = 0.0
+        for (n, p), q in zip(model.named_parameters(), replica.parameters()):
+            scale = q.grad.abs().max().item() + 1e-30
+            worst = max(worst, (p.grad - q.grad).abs().max().item() / scale)
+        rm = max((a - b).abs().max().item() for (na, a), (nb, b) in zip(model.named_buffers(), replica.named_buffers()) if "running" in na)
+        assert worst < 2e-3 and rm < 1e-4, (worst, rm)
+        if rank == 0:
+            print(f"DDP-OK syncbn world={world} worst_rel={worst:.2e} running_stat_diff={rm:.2e}")
+        dist.destroy_process_group()
+        return
     replica(x, mask)[0].pow(2).mean().backward()
     nbytes, worst = 0, 0.0
     for (n, p), q in zip(model.named_parameters(), replica.parameters()):

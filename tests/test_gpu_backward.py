@@ -302,3 +302,8 @@ def test_ddp_gradient_allreduce_two_ranks(dev):
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "ddp_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DDP-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    # train.py:31 sync_batchnorm=True: conv_module.norm converted to SyncBatchNorm -- cross-rank batch statistics
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29534", os.path.join(root, "tests", "ddp_worker.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, AVSR_DDP_SYNCBN="1", AVSR_DDP_BLOCKS="2"))
+    assert r.returncode == 0 and "DDP-OK syncbn" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
