@@ -23,6 +23,7 @@ def main():
     # sees the same forward; each rank gets its own bucket (train.py:34-37: one bucket per rank per step)
     nblocks = int(os.environ.get("AVSR_DDP_BLOCKS", "12"))
     kw = dict(num_blocks=nblocks, dropout_rate=0.0, positional_dropout_rate=0.0, attention_dropout_rate=0.0)
+    os.environ.setdefault("AVSR_B200_PRECISION", "fp32" if os.environ.get("AVSR_DDP_SYNCBN", "0") == "1" else "f16")
     torch.manual_seed(0)
     model = ConformerEncoder(**kw).to(dev).train()
     replica = ConformerEncoder(**kw).to(dev).train()
@@ -41,10 +42,12 @@ def main():
         # every rank rebuilds that: gather the inputs, run the un-wrapped BatchNorm1d replica on the concatenated batch
         # with the global-mean loss, and compare its gradients with DDP's (mean over ranks of the per-rank losses)
         xs_all = [torch.empty_like(x) for _ in range(world)]
-        ms_all = [torch.empty_like(mask) for _ in range(world)]
+        ln = torch.tensor(lengths, device=dev, dtype=torch.int64)
+        ln_all = [torch.empty_like(ln) for _ in range(world)]
         dist.all_gather(xs_all, x)
-        dist.all_gather(ms_all, mask)
-        out = replica(torch.cat(xs_all), torch.cat(ms_all))[0]
+        dist.all_gather(ln_all, ln)
+        mask_all = (torch.arange(100, device=dev)[None, :] < torch.cat(ln_all)[:, None]).unsqueeze(1)
+        out = replica(torch.cat(xs_all), mask_all)[0]
         (out.pow(2).mean()).backward()
         worst = 0.0
         for (n, p), q in zip(model.named_parameters(), replica.parameters()):
@@ -72,4 +75,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:          # noqa: BLE001 -- torchrun swallows the child's stderr tail: put the traceback on stdout
+        import traceback
+        print("DDP-WORKER-FAILED rank", os.environ.get("RANK"), traceback.format_exc(), flush=True)
+        raise
