@@ -50,8 +50,10 @@ def main():
         out = replica(torch.cat(xs_all), mask_all)[0]
         (out.pow(2).mean()).backward()
         worst = 0.0
+        gscale = max(q.grad.abs().max().item() for q in replica.parameters())
         for (n, p), q in zip(model.named_parameters(), replica.parameters()):
-            scale = q.grad.abs().max().item() + 1e-30
+            # (biases in front of a normalisation / of the keys have mathematically zero gradients: floor the scale)
+            scale = q.grad.abs().max().item() + 1e-4 * gscale
             worst = max(worst, (p.grad - q.grad).abs().max().item() / scale)
         rm = max((a - b).abs().max().item() for (na, a), (nb, b) in zip(model.named_buffers(), replica.named_buffers()) if "running" in na)
         assert worst < 2e-3 and rm < 1e-4, (worst, rm)
@@ -67,7 +69,7 @@ def main():
         ref /= world
         nbytes += p.grad.numel() * 4
         scale = ref.abs().max().item() + 1e-30
-        worst = max(worst, (p.grad - ref).abs().max().item() / scale)
+        worst = max(worst, (p.grad - ref).abs().max().item() / scale)   # same arithmetic on both sides: exact up to NCCL's sum order
     assert worst < 1e-4, worst
     if rank == 0:
         print(f"DDP-OK world={world} grad_bytes={nbytes} worst_rel={worst:.2e}")
