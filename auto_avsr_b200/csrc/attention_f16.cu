@@ -14,8 +14,6 @@
 //     maximum: probabilities are exp2(s - ref), and only when a tile's maximum exceeds ref by more than 2^8 the row's
 //     O columns (tcgen05.ld / st) and running sum are rescaled and ref moves -- p stays <= 256 (exact in fp16/fp32
 //     terms: the final O / l is the same softmax), and after the first tiles rescales are rare;
-//   * the softmax warps pull a tile's S and G into registers first and release the columns at once, so the MMA warp
-//     computes the NEXT tile's scores while they work: no second S/G buffer, no MMA round trip on the critical path;
 //   * the context tile leaves through shared memory and ONE TMA store (3-D map, rows beyond T are clipped) instead of
 //     8-byte lane-per-row stores.
 //
@@ -81,7 +79,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
   uint8_t* gen = a2_smem_raw + (base - raw);
   const uint32_t bars = base + A2_BARS;
   const uint32_t q_full = bars, kp_full = bars + 8, v_full = bars + 16, s_full = bars + 24, p_full = bars + 32,
-                 o_full = bars + 40, sg_free = bars + 48;
+                 o_full = bars + 40;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + A2_BARS + 64);
   float* xch = reinterpret_cast<float*>(gen + A2_XCH);
 
@@ -105,7 +103,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
     tma_prefetch_desc(&tmQu); tma_prefetch_desc(&tmQv); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmP); tma_prefetch_desc(&tmCtx);
     mbar_init(q_full, 1); mbar_init(kp_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1);
-    mbar_init(p_full, 256); mbar_init(o_full, 1); mbar_init(sg_free, 256);
+    mbar_init(p_full, 256); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
@@ -120,41 +118,26 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
-    // Two independent chains share this warp: K / Pband(t) may be loaded once the S/G MMAs of tile t-1 retired (s_full),
-    // V(t) once P.V(t-1) retired (o_full).  S/G(t) run a tile AHEAD of the softmax, so the chains advance at different
-    // times: poll both barriers and serve whichever is ready (a barrier cannot run ahead of the load it is waiting for,
-    // so the polled parity is unambiguous).
     if (nkt > 0) {
-      auto load_kp = [&](int it) {
-        if (elect_one_sync()) {
-          const int j0 = it * A2_BKV;
-          mbar_expect_tx(kp_full, A2_BKV * 128 + A2_BAND * 128);
-          tma_load_2d(base + A2_K, &tmK, 0, bh * T + j0, kp_full);
-          const int m_lo = j0 - i0 - (A2_BQ - 1) + T - 1;     // first table row of the band (may be < 0: zero fill)
-          tma_load_3d(base + A2_PB, &tmP, 0, m_lo, h, kp_full);
-        }
-      };
-      auto load_v = [&](int it) {
-        if (elect_one_sync()) {
-          mbar_expect_tx(v_full, A2_BKV * 128);
-          tma_load_2d(base + A2_V, &tmV, 0, bh * T + it * A2_BKV, v_full);
-        }
-      };
       if (elect_one_sync()) {
         mbar_expect_tx(q_full, 2 * A2_BQ * 128);
         tma_load_2d(base + A2_QU, &tmQu, 0, bh * T + i0, q_full);
         tma_load_2d(base + A2_QV, &tmQv, 0, bh * T + i0, q_full);
       }
-      load_kp(0);
-      load_v(0);
-      int kn = 1, vn = 1;                                     // next tile of each chain
-      uint32_t spins = 0;
-      while (kn < nkt || vn < nkt) {
-        bool progress = false;
-        if (kn < nkt && mbar_try_wait(s_full, (kn - 1) & 1)) { load_kp(kn); ++kn; progress = true; }
-        if (vn < nkt && mbar_try_wait(o_full, (vn - 1) & 1)) { load_v(vn); ++vn; progress = true; }
-        if (progress) spins = 0;
-        else if (++spins > (1u << 24)) __trap();              // protocol bug: fail the launch instead of hanging
+      for (int it = 0; it < nkt; ++it) {
+        const int j0 = it * A2_BKV;
+        if (it > 0) mbar_wait(s_full, (it - 1) & 1);          // S/G MMAs of the previous tile retired: K, Pband free
+        if (elect_one_sync()) {
+          mbar_expect_tx(kp_full, A2_BKV * 128 + A2_BAND * 128);
+          tma_load_2d(base + A2_K, &tmK, 0, bh * T + j0, kp_full);
+          const int m_lo = j0 - i0 - (A2_BQ - 1) + T - 1;     // first table row of the band (may be < 0: zero fill)
+          tma_load_3d(base + A2_PB, &tmP, 0, m_lo, h, kp_full);
+        }
+        if (it > 0) mbar_wait(o_full, (it - 1) & 1);          // P.V of the previous tile retired: V free
+        if (elect_one_sync()) {
+          mbar_expect_tx(v_full, A2_BKV * 128);
+          tma_load_2d(base + A2_V, &tmV, 0, bh * T + j0, v_full);
+        }
       }
     }
   } else if (warp == 1) {
@@ -185,16 +168,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       issue_scores();
       AVSR_TRACE_MARK(lane == 0, trc, 2);
       for (int it = 0; it < nkt; ++it) {
-        if (it + 1 < nkt) {
-          // the softmax warps pull S/G(it) into registers at the START of their tile and release the columns at once
-          // (sg_free): the next tile's scores are computed while they work on this one -- the MMA round trip left the
-          // per-tile critical path without a second S/G buffer
-          mbar_wait(sg_free, it & 1);
-          mbar_wait(kp_full, (it + 1) & 1);
-          tc_fence_after();
-          issue_scores();
-        }
-        mbar_wait(p_full, it & 1);   // softmax rescaled O if needed and published P(it)
+        mbar_wait(p_full, it & 1);   // softmax consumed S/G(it), rescaled O if needed and published P(it)
         mbar_wait(v_full, it & 1);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -202,6 +176,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
           mma_f16(t_o, d_p, d_v, idesc_o, it != 0);
           mma_f16(t_o, d_p + 2, d_v + 128, idesc_o, 1);
           tc_commit(o_full);
+        }
+        if (it + 1 < nkt) {
+          mbar_wait(kp_full, (it + 1) & 1);
+          tc_fence_after();
+          issue_scores();
         }
       }
     }
@@ -220,7 +199,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
 
     for (int it = 0; it < nkt; ++it) {
       if (!warp_valid) {            // nothing to compute or store: keep the barrier protocol going, one phase at a time
-        mbar_arrive(sg_free);
         mbar_arrive(p_full);
         mbar_wait(o_full, it & 1);
         continue;
@@ -231,7 +209,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       AVSR_TRACE_MARK(it == 0 && threadIdx.x == 64, trc, 3);
       float s[16];   // raw (unscaled) scores of this thread's 16 keys
       if (jc >= L) {                              // chunk entirely beyond the utterance: no loads, no skew
-        mbar_arrive(sg_free);
 #pragma unroll
         for (int c = 0; c < 16; ++c) s[c] = -INFINITY;
       } else {
@@ -240,8 +217,6 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
         tmem_ld16(trow + T2_G + gbase + hf * 16 + 32, x + 32);
         tmem_ld16(trow + T2_S + hf * 16, s);
         tmem_ld_wait();
-        tc_fence_before();                        // S/G(it) are in registers: the MMA warp may overwrite the columns
-        mbar_arrive(sg_free);
         // y[c] = x[c + sh], sh in [0,31]: barrel shifter, one stage per bit of sh, as per-element selects (in-place is
         // safe in increasing c: x[c + 2^k] is still the previous stage's value)
         {
@@ -276,15 +251,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmQu, const __grid_cons
       const bool move = tmax > t_ref + kRescaleLog2;   // same decision in both threads of the row (same tmax, same t_ref)
       const float alpha = move ? ex2_fast(t_ref - tmax) : 1.0f;            // first tile: exp2(-inf) = 0
       if (move) { l_run *= alpha; t_ref = tmax; }
-      // P.V(it-1) is issued AFTER S/G(it) now, so observing S/G(it) no longer implies that it retired: wait for it before
-      // touching what it reads / writes -- the P tile in shared memory (overwritten below) and O (rescaled here).  By
-      // the time a thread gets here the MMA (issued when the previous tile's P was published) has normally retired.
-      if (it > 0) {
-        mbar_wait(o_full, (it - 1) & 1);
-        tc_fence_after();
-      }
       // tcgen05.ld / st are warp-collective (.sync.aligned): when ANY row of the warp moves its reference, the whole
-      // warp rescales its 32 x 32 block of O in tensor memory (alpha = 1 for the rows that stay).
+      // warp rescales its 32 x 32 block of O in tensor memory (alpha = 1 for the rows that stay).  P.V(it-1) has
+      // retired: S/G(it), which we just observed, were issued after it.
       if (it > 0 && __any_sync(0xffffffffu, move)) {
         float ov[32];
         tmem_ld32(trow + T2_O + hf * 32, ov);
