@@ -303,31 +303,32 @@ int launch_sinusoid(void* pe, int T, int d, int out_kind, cudaStream_t st) {
 // y[b,t,c] = silu( (sum_k wt[k][c] * x[b, t+k-half, c]) * scale[c] + shift[c] ),  x zero outside [0,T) per
 // utterance row b -- no length mask: padded frames are data (conformer_encoder.py:30-35).
 // scale/shift fold the depthwise bias and the BatchNorm running statistics (avsr_prepare_weights).
-// Tile: 64 channels x 64 frames per CTA (128 threads); the (64+K-1) x 64 input patch and the K x 64 taps are staged
+// Tile: CH channels x 64 frames per CTA; the (64+K-1) x CH input patch and the K x CH taps are staged
 // in shared memory with coalesced float4 loads along the channel axis.  Each thread produces 8 consecutive frames of
 // one channel quad with a register sliding window: per tap ONE new input row and one tap vector are read from
 // shared memory for 8 outputs (the v1 kernel read 2 per output pair: 4x more shared-memory traffic, r01 profile).
-constexpr int kDwCh = 64;    // channels per CTA (16 quads)
 constexpr int kDwTT = 64;    // frames per CTA
 constexpr int kDwFr = 8;     // frames per thread
-constexpr int kDwThreads = (kDwCh / 4) * (kDwTT / kDwFr);   // 128
+// channels per CTA (CH) is a launch-time choice: 64 (16 quads, 128 threads, 336 CTAs at S2) or 32 (8 quads, 64 threads,
+// 672 CTAs: the same halo ratio and full 128-byte row segments, twice as many CTAs in flight per SM to hide the
+// load -> barrier -> compute -> store chain of each)
 
-template <int K>
+template <int K, int QPR>
 __device__ __forceinline__ void dw_accumulate(const float4* in_s, const float4* w_s, int q, int ts, int k_runtime,
                                               float4 (&acc)[kDwFr]) {
   // K > 0: fully unrolled (window shifts become register renames); K == 0: runtime tap count
   constexpr int KK = K > 0 ? K : 1;
   float4 win[kDwFr];
 #pragma unroll
-  for (int j = 0; j < kDwFr - 1; ++j) win[j + 1] = in_s[(ts * kDwFr + j) * 16 + q];
+  for (int j = 0; j < kDwFr - 1; ++j) win[j + 1] = in_s[(ts * kDwFr + j) * QPR + q];
   const int taps = K > 0 ? KK : k_runtime;
 #pragma unroll
   for (int k = 0; k < (K > 0 ? KK : 256); ++k) {
     if (K == 0 && k >= taps) break;
 #pragma unroll
     for (int j = 0; j < kDwFr - 1; ++j) win[j] = win[j + 1];
-    win[kDwFr - 1] = in_s[(ts * kDwFr + kDwFr - 1 + k) * 16 + q];
-    const float4 w = w_s[k * 16 + q];
+    win[kDwFr - 1] = in_s[(ts * kDwFr + kDwFr - 1 + k) * QPR + q];
+    const float4 w = w_s[k * QPR + q];
 #pragma unroll
     for (int j = 0; j < kDwFr; ++j) {
       acc[j].x = fmaf(w.x, win[j].x, acc[j].x); acc[j].y = fmaf(w.y, win[j].y, acc[j].y);
@@ -336,19 +337,20 @@ __device__ __forceinline__ void dw_accumulate(const float4* in_s, const float4* 
   }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt,
-                                                                    const float* __restrict__ scale,
-                                                                    const float* __restrict__ shift, void* __restrict__ y,
-                                                                    int T, int C, int k_runtime, int out_kind) {
+template <int K, int CH>
+__global__ void __launch_bounds__((CH / 4) * (kDwTT / kDwFr))
+dwconv_bn_silu_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ scale,
+                      const float* __restrict__ shift, void* __restrict__ y, int T, int C, int k_runtime, int out_kind) {
+  constexpr int QPR = CH / 4;                                // float4 quads per staged row
+  constexpr int NT = QPR * (kDwTT / kDwFr);                  // threads per CTA
   extern __shared__ float4 dw_smem[];
   pdl_launch_dependents();
-  AVSR_TSPAN_OPEN(120, 0);
+  AVSR_TSPAN_OPEN(120, CH);
   const int Kt = K > 0 ? K : k_runtime;
   const int rows_in = kDwTT + Kt - 1;
-  float4* in_s = dw_smem;                          // [rows_in][16]
-  float4* w_s = dw_smem + rows_in * (kDwCh / 4);   // [K][16]
-  const int c0 = blockIdx.x * kDwCh;
+  float4* in_s = dw_smem;                          // [rows_in][QPR]
+  float4* w_s = dw_smem + rows_in * QPR;           // [K][QPR]
+  const int c0 = blockIdx.x * CH;
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
   const int half = (Kt - 1) >> 1;
@@ -356,8 +358,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
   const float* xb = x + (long)b * T * C;
 
   // the taps are parameters: stage them before waiting on the producer of x
-  for (int i = tid; i < Kt * (kDwCh / 4); i += kDwThreads) {
-    const int k = i >> 4, q = i & 15;
+  for (int i = tid; i < Kt * QPR; i += NT) {
+    const int k = i / QPR, q = i % QPR;
     const int c = c0 + q * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) v = *reinterpret_cast<const float4*>(wt + (long)k * C + c);
@@ -366,33 +368,33 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
   pdl_wait();
   AVSR_TSPAN_DEP();
   {
-    const int total = rows_in * (kDwCh / 4);
-    for (int i0 = tid; i0 < total; i0 += 4 * kDwThreads) {   // 4 independent 16-byte loads in flight per thread
+    const int total = rows_in * QPR;
+    for (int i0 = tid; i0 < total; i0 += 4 * NT) {   // 4 independent 16-byte loads in flight per thread
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kDwThreads;
-        const int r = i >> 4, q = i & 15;
+        const int i = i0 + u * NT;
+        const int r = i / QPR, q = i % QPR;
         const int t = t0 - half + r, c = c0 + q * 4;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < total && t >= 0 && t < T && c < C) v[u] = *reinterpret_cast<const float4*>(xb + (long)t * C + c);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kDwThreads;
+        const int i = i0 + u * NT;
         if (i < total) in_s[i] = v[u];
       }
     }
   }
   __syncthreads();
 
-  const int q = tid & 15, ts = tid >> 4;           // channel quad, group of 8 frames
+  const int q = tid % QPR, ts = tid / QPR;         // channel quad, group of 8 frames
   const int c = c0 + q * 4;
   if (c >= C) return;
   float4 acc[kDwFr];
 #pragma unroll
   for (int j = 0; j < kDwFr; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  dw_accumulate<K>(in_s, w_s, q, ts, k_runtime, acc);
+  dw_accumulate<K, QPR>(in_s, w_s, q, ts, k_runtime, acc);
   const float4 sc = *reinterpret_cast<const float4*>(scale + c);
   const float4 sh = *reinterpret_cast<const float4*>(shift + c);
 #pragma unroll
@@ -413,20 +415,27 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bn_silu_kernel(const float*
   AVSR_TSPAN_CLOSE();
 }
 
+template <int K, int CH>
+static int launch_dw(const float* x, const float* wt, const float* scale, const float* shift, void* y, int B, int T, int C, int Kr,
+                     int out_kind, cudaStream_t st) {
+  const size_t smem = (size_t)(kDwTT + Kr - 1 + Kr) * (CH / 4) * sizeof(float4);
+  dim3 grid(cdiv(C, CH), cdiv(T, kDwTT), B);
+  if (smem > 48 * 1024)
+    AVSR_CUDA_TRY(cudaFuncSetAttribute((dwconv_bn_silu_kernel<K, CH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AVSR_LAUNCH((dwconv_bn_silu_kernel<K, CH>), grid, (CH / 4) * (kDwTT / kDwFr), smem, st, x, wt, scale, shift, y, T, C, Kr, out_kind);
+  return AVSR_OK;
+}
+
 int launch_dwconv_bn_silu(const float* x, const float* wt, const float* scale, const float* shift, void* y, int B,
                           int T, int C, int K, int out_kind, cudaStream_t st) {
   AVSR_REQUIRE(C % 4 == 0 && K % 2 == 1 && K >= 1 && K <= 255, "dwconv: C=%d must be a multiple of 4, K=%d odd", C, K);
   if (B <= 0 || T <= 0) return AVSR_OK;
-  const size_t smem = (size_t)(kDwTT + K - 1 + K) * (kDwCh / 4) * sizeof(float4);
-  dim3 grid(cdiv(C, kDwCh), cdiv(T, kDwTT), B);
+  static const int ch = [] { const char* e = getenv("AVSR_B200_DW"); return (e && atoi(e) == 64) ? 64 : 32; }();
   if (K == 31) {   // the reference's cnn_module_kernel (e2e_asr_conformer.py:38): fully unrolled taps
-    AVSR_LAUNCH(dwconv_bn_silu_kernel<31>, grid, kDwThreads, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
-  } else {
-    if (smem > 48 * 1024)
-      AVSR_CUDA_TRY(cudaFuncSetAttribute(dwconv_bn_silu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AVSR_LAUNCH(dwconv_bn_silu_kernel<0>, grid, kDwThreads, smem, st, x, wt, scale, shift, y, T, C, K, out_kind);
+    return ch == 64 ? launch_dw<31, 64>(x, wt, scale, shift, y, B, T, C, K, out_kind, st)
+                    : launch_dw<31, 32>(x, wt, scale, shift, y, B, T, C, K, out_kind, st);
   }
-  return AVSR_OK;
+  return launch_dw<0, 64>(x, wt, scale, shift, y, B, T, C, K, out_kind, st);
 }
 
 }  // namespace avsr

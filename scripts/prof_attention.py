@@ -12,7 +12,7 @@ B, T, H = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (4, 400, 12)
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(5)
 D = H * 64
-q, k, v = (torch.randn(B, T, D, generator=g).to(dev) for _ in range(3))
+q, k, v = ((torch.randn(B, T, D, generator=g) * 0.5).to(dev) for _ in range(3))      # moderate logits: few reference moves
 p = torch.randn(2 * T - 1, D, generator=g).to(dev)
 u, vb = (torch.randn(H, 64, generator=g) * 0.3).to(dev), (torch.randn(H, 64, generator=g) * 0.3).to(dev)
 for _ in range(4):
