@@ -89,9 +89,11 @@ def test_no_cpu_fallback(built):
         LayerNorm(768)(torch.zeros(2, 768))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         PositionwiseFeedForward(768, 3072, 0.1).eval()(torch.zeros(2, 768))
-    enc.train()
-    with pytest.raises(NotImplementedError, match="inference forward only"):
+    enc.train()                                   # training runs in the library too (round 2): still no CPU path
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc(torch.zeros(1, 8, 768), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PositionwiseFeedForward(768, 3072, 0.1).train()(torch.zeros(2, 768))
 
 
 def test_missing_library_fails_loudly(built):
