@@ -9,9 +9,9 @@
 //   rows kernel  (one warp per query row)      : log-sum-exp and Delta of the row, then the two parts of dq
 //   keys kernel  (one warp per key)            : dk, dv
 //   pos kernel   (one warp per (table row, h)) : dp
-// A lane owns one (row, key) pair at a time: its 64-element dot products read the pair's vectors straight from global
-// memory (256 contiguous bytes per lane, L1-resident across the 16 float4 steps) against the warp's own vector in
-// shared memory (broadcast reads).  Every output element is written by exactly one warp: no atomics, deterministic.
+// A lane owns one (row, key) pair at a time; the vectors it needs are staged tile by tile in shared memory by the whole CTA
+// (r02 profile of the first version, whose lanes read their rows straight from global memory: 81 % of the training
+// step).  Every output element is written by exactly one warp: no atomics, deterministic.
 // q, k, v, ctx, dctx and the outputs are (B, T, H*64); p / dp are (2T-1, H*64); u, v (H, 64).
 #include <math.h>
 
@@ -19,40 +19,56 @@
 
 namespace avsr {
 
-constexpr int kAbWarps = 4;
+constexpr int kAbWarps = 8;          // warps per CTA = output rows per CTA (query rows / keys / table rows)
+constexpr int kAbTile = 32;          // the other index is walked in tiles of 32 (one per lane)
+constexpr int kAbPitch = 68;         // floats per staged row: 64 + 4 pad -> lane-per-row float4 reads are conflict-free
+constexpr int kAbBand = kAbTile + kAbWarps - 1;   // 39 rel-pos / shifted rows a (tile, 8 rows) pair touches
+constexpr int kPosSmemBytes = ((3 * kAbTile + 2 * kAbBand) * kAbPitch + kAbWarps * 64 + 2 * kAbTile) * (int)sizeof(float);
 
-__device__ __forceinline__ float dot64(const float* __restrict__ smem_vec, const float* __restrict__ row) {
-  float acc = 0.f;
-#pragma unroll
-  for (int t = 0; t < 16; ++t) {
-    const float4 a = reinterpret_cast<const float4*>(smem_vec)[t];
-    const float4 b = reinterpret_cast<const float4*>(row)[t];
-    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+// Stage `nrows` rows of 64 floats (global row r at base + r * row_stride) into shared memory, pitch kAbPitch; rows
+// outside [lo, hi) are zero.  All threads of the CTA take part (coalesced: 16 float4 per row).
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ base, long row_stride, int first, int nrows,
+                                           int lo, int hi) {
+  for (int idx = threadIdx.x; idx < nrows * 16; idx += blockDim.x) {
+    const int r = idx >> 4, t = idx & 15;
+    const int g = first + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= lo && g < hi) v = reinterpret_cast<const float4*>(base + (long)g * row_stride)[t];
+    reinterpret_cast<float4*>(dst + r * kAbPitch)[t] = v;
   }
-  return acc;
 }
-// dot of two global rows where the first one gets a bias vector (shared memory) added: (a + bias) . c
-__device__ __forceinline__ float dot64_biased(const float* __restrict__ a, const float* __restrict__ bias,
-                                              const float* __restrict__ c) {
+// the same with a bias vector (64 floats, global) added to every valid row
+__device__ __forceinline__ void stage_rows_biased(float* dst, const float* __restrict__ base, long row_stride, int first,
+                                                  int nrows, int lo, int hi, const float* __restrict__ bias) {
+  for (int idx = threadIdx.x; idx < nrows * 16; idx += blockDim.x) {
+    const int r = idx >> 4, t = idx & 15;
+    const int g = first + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= lo && g < hi) {
+      v = reinterpret_cast<const float4*>(base + (long)g * row_stride)[t];
+      const float4 c = reinterpret_cast<const float4*>(bias)[t];
+      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    }
+    reinterpret_cast<float4*>(dst + r * kAbPitch)[t] = v;
+  }
+}
+
+// dot of two shared-memory vectors of 64 floats (a: broadcast across the warp, b: this lane's row)
+__device__ __forceinline__ float sdot64(const float* a, const float* b) {
   float acc = 0.f;
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     const float4 x = reinterpret_cast<const float4*>(a)[t];
-    const float4 b = reinterpret_cast<const float4*>(bias)[t];
-    const float4 y = reinterpret_cast<const float4*>(c)[t];
-    acc = fmaf(x.x + b.x, y.x, acc); acc = fmaf(x.y + b.y, y.y, acc); acc = fmaf(x.z + b.z, y.z, acc); acc = fmaf(x.w + b.w, y.w, acc);
+    const float4 y = reinterpret_cast<const float4*>(b)[t];
+    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
   }
   return acc;
 }
-// acc[0..63] += s * (row[0..63] (+ bias))
-__device__ __forceinline__ void axpy64(float (&acc)[64], float s, const float* __restrict__ row, const float* bias) {
+// acc[0..63] += s * row[0..63]   (row in shared memory)
+__device__ __forceinline__ void saxpy64(float (&acc)[64], float s, const float* row) {
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
-    float4 b = reinterpret_cast<const float4*>(row)[t];
-    if (bias) {
-      const float4 c = reinterpret_cast<const float4*>(bias)[t];
-      b.x += c.x; b.y += c.y; b.z += c.z; b.w += c.w;
-    }
+    const float4 b = reinterpret_cast<const float4*>(row)[t];
     acc[4 * t] = fmaf(s, b.x, acc[4 * t]); acc[4 * t + 1] = fmaf(s, b.y, acc[4 * t + 1]);
     acc[4 * t + 2] = fmaf(s, b.z, acc[4 * t + 2]); acc[4 * t + 3] = fmaf(s, b.w, acc[4 * t + 3]);
   }
@@ -68,48 +84,61 @@ __device__ __forceinline__ float2 reduce64(float (&acc)[64], int lane) {
   return make_float2(lo, hi);
 }
 
+// Every kernel: a CTA owns kAbWarps consecutive output rows (one per warp) and walks the other index in tiles of 32 that
+// the whole CTA stages in shared memory once (K / V / Q / dctx tiles of 32 rows, the 39-row band of the rel-pos table
+// or of the shifted keys): 8x less L2 traffic than one warp streaming its own rows, and conflict-free shared reads.
+
 // ---------------------------------------------------------------- rows: lse, Delta, dq (k part / p part)
 __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_rows_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ p,
     const float* __restrict__ u, const float* __restrict__ vb, const int32_t* __restrict__ lengths,
     const float* __restrict__ ctx, const float* __restrict__ dctx, float* __restrict__ lse, float* __restrict__ delta,
     float* __restrict__ dq_k, float* __restrict__ dq_p, int T, int H) {
-  __shared__ __align__(16) float sm[kAbWarps][3][64];
+  __shared__ __align__(16) float Ks[kAbTile * kAbPitch], Vs[kAbTile * kAbPitch], Ps[kAbBand * kAbPitch];
+  __shared__ __align__(16) float vec[kAbWarps][3][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * kAbWarps + warp, h = blockIdx.y, b = blockIdx.z;
-  if (i >= T) return;
-  const int D = H * kHeadDim;
+  const int i0 = blockIdx.x * kAbWarps, i = i0 + warp, h = blockIdx.y, b = blockIdx.z;
+  const bool active = i < T;
+  const int D = H * kHeadDim, R = 2 * T - 1;
   int L = T;
   if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }
-  const long ro = ((long)b * T + i) * D + h * kHeadDim;
-  float* qu = sm[warp][0];
-  float* qv = sm[warp][1];
-  float* dc = sm[warp][2];
+  const long ro = ((long)b * T + (active ? i : 0)) * D + h * kHeadDim;
+  float* qu = vec[warp][0];
+  float* qv = vec[warp][1];
+  float* dc = vec[warp][2];
   float dl = 0.f;
-  for (int d = lane; d < 64; d += 32) {
-    const float qq = q[ro + d];
-    qu[d] = qq + u[h * 64 + d];
-    qv[d] = qq + vb[h * 64 + d];
-    dc[d] = dctx[ro + d];
-    dl += dctx[ro + d] * ctx[ro + d];
+  if (active) {
+    for (int d = lane; d < 64; d += 32) {
+      const float qq = q[ro + d];
+      qu[d] = qq + u[h * 64 + d];
+      qv[d] = qq + vb[h * 64 + d];
+      dc[d] = dctx[ro + d];
+      dl += dctx[ro + d] * ctx[ro + d];
+    }
+    dl = warp_sum(dl);
   }
-  dl = warp_sum(dl);
-  __syncwarp();
   const float* kb = k + (long)b * T * D + h * kHeadDim;
   const float* vbase = v + (long)b * T * D + h * kHeadDim;
   const float* pb = p + h * kHeadDim;
   // pass 1: online log-sum-exp of the row
   float m = -INFINITY, ssum = 0.f;
-  for (int j0 = 0; j0 < L; j0 += 32) {
-    const int j = j0 + lane;
-    float s = -INFINITY;
-    if (j < L) s = 0.125f * (dot64(qu, kb + (long)j * D) + dot64(qv, pb + (long)(j - i + T - 1) * D));
-    const float mn = fmaxf(m, warp_max(s));
-    ssum = ssum * __expf(m - mn) + warp_sum(j < L ? __expf(s - mn) : 0.f);
-    m = mn;
+  for (int j0 = 0; j0 < L; j0 += kAbTile) {
+    const int mb = j0 - (i0 + kAbWarps - 1) + T - 1;          // table row of (key j0, last query row of the CTA)
+    __syncthreads();
+    stage_rows(Ks, kb, D, j0, kAbTile, 0, L);
+    stage_rows(Ps, pb, D, mb, kAbBand, 0, R);
+    __syncthreads();
+    if (active) {
+      const int j = j0 + lane;
+      float s = -INFINITY;
+      if (j < L) s = 0.125f * (sdot64(qu, Ks + lane * kAbPitch) + sdot64(qv, Ps + (j - i + T - 1 - mb) * kAbPitch));
+      const float mn = fmaxf(m, warp_max(s));
+      ssum = ssum * __expf(m - mn) + warp_sum(j < L ? __expf(s - mn) : 0.f);
+      m = mn;
+    }
   }
   const float row_lse = L > 0 ? m + logf(ssum) : INFINITY;     // len 0: exp(s - inf) = 0 below
-  if (lane == 0) {
+  if (active && lane == 0) {
     lse[((long)b * H + h) * T + i] = row_lse;
     delta[((long)b * H + h) * T + i] = dl;
   }
@@ -117,18 +146,25 @@ __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_rows_kernel(
   float ak[64], ap[64];
 #pragma unroll
   for (int d = 0; d < 64; ++d) ak[d] = ap[d] = 0.f;
-  for (int j0 = 0; j0 < L; j0 += 32) {
+  for (int j0 = 0; j0 < L; j0 += kAbTile) {
+    const int mb = j0 - (i0 + kAbWarps - 1) + T - 1;
+    __syncthreads();
+    stage_rows(Ks, kb, D, j0, kAbTile, 0, L);
+    stage_rows(Vs, vbase, D, j0, kAbTile, 0, L);
+    stage_rows(Ps, pb, D, mb, kAbBand, 0, R);
+    __syncthreads();
     const int j = j0 + lane;
-    if (j < L) {
-      const float* kr = kb + (long)j * D;
-      const float* pr = pb + (long)(j - i + T - 1) * D;
-      const float s = 0.125f * (dot64(qu, kr) + dot64(qv, pr));
+    if (active && j < L) {
+      const float* kr = Ks + lane * kAbPitch;
+      const float* pr = Ps + (j - i + T - 1 - mb) * kAbPitch;
+      const float s = 0.125f * (sdot64(qu, kr) + sdot64(qv, pr));
       const float a = __expf(s - row_lse);
-      const float g = a * (dot64(dc, vbase + (long)j * D) - dl) * 0.125f;
-      axpy64(ak, g, kr, nullptr);
-      axpy64(ap, g, pr, nullptr);
+      const float g = a * (sdot64(dc, Vs + lane * kAbPitch) - dl) * 0.125f;
+      saxpy64(ak, g, kr);
+      saxpy64(ap, g, pr);
     }
   }
+  if (!active) return;
   const float2 rk = reduce64(ak, lane), rp = reduce64(ap, lane);
   dq_k[ro + lane] = rk.x; dq_k[ro + lane + 32] = rk.y;
   dq_p[ro + lane] = rp.x; dq_p[ro + lane + 32] = rp.y;
@@ -140,25 +176,20 @@ __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_keys_kernel(
     const float* __restrict__ u, const float* __restrict__ vb, const int32_t* __restrict__ lengths,
     const float* __restrict__ dctx, const float* __restrict__ lse, const float* __restrict__ delta,
     float* __restrict__ dk, float* __restrict__ dv, int T, int H) {
-  __shared__ __align__(16) float sm[kAbWarps][4][64];
+  __shared__ __align__(16) float Qu[kAbTile * kAbPitch], Qv[kAbTile * kAbPitch], Dc[kAbTile * kAbPitch], Ps[kAbBand * kAbPitch];
+  __shared__ __align__(16) float vec[kAbWarps][2][64];
+  __shared__ float ls[kAbTile], ds[kAbTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * kAbWarps + warp, h = blockIdx.y, b = blockIdx.z;
-  if (j >= T) return;
-  const int D = H * kHeadDim;
+  const int j0 = blockIdx.x * kAbWarps, j = j0 + warp, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * kHeadDim, R = 2 * T - 1;
   int L = T;
   if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }
-  const long ko = ((long)b * T + j) * D + h * kHeadDim;
-  if (j >= L) {                                   // masked key: it received no probability
-    dk[ko + lane] = 0.f; dk[ko + lane + 32] = 0.f;
-    dv[ko + lane] = 0.f; dv[ko + lane + 32] = 0.f;
-    return;
-  }
-  float* kj = sm[warp][0];
-  float* vj = sm[warp][1];
-  float* su = sm[warp][2];
-  float* sv = sm[warp][3];
-  for (int d = lane; d < 64; d += 32) { kj[d] = k[ko + d]; vj[d] = v[ko + d]; su[d] = u[h * 64 + d]; sv[d] = vb[h * 64 + d]; }
-  __syncwarp();
+  const bool active = j < L;                       // a masked key (or j >= T) received no probability: zeros
+  const long ko = ((long)b * T + (j < T ? j : 0)) * D + h * kHeadDim;
+  float* kj = vec[warp][0];
+  float* vj = vec[warp][1];
+  if (j < T)
+    for (int d = lane; d < 64; d += 32) { kj[d] = k[ko + d]; vj[d] = v[ko + d]; }
   const float* qb = q + (long)b * T * D + h * kHeadDim;
   const float* db_ = dctx + (long)b * T * D + h * kHeadDim;
   const float* pb = p + h * kHeadDim;
@@ -167,18 +198,33 @@ __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_keys_kernel(
   float ak[64], av[64];
 #pragma unroll
   for (int d = 0; d < 64; ++d) ak[d] = av[d] = 0.f;
-  for (int i0 = 0; i0 < T; i0 += 32) {
-    const int i = i0 + lane;
-    if (i < T) {
-      const float* qr = qb + (long)i * D;
-      const float* dr = db_ + (long)i * D;
-      const float s = 0.125f * (dot64_biased(qr, su, kj) + dot64_biased(qr, sv, pb + (long)(j - i + T - 1) * D));
-      const float a = __expf(s - lrow[i]);
-      const float g = a * (dot64(vj, dr) - drow[i]) * 0.125f;
-      axpy64(av, a, dr, nullptr);
-      axpy64(ak, g, qr, su);
+  if (j0 < L) {                                    // CTA-uniform: at least one key of this CTA is valid
+    for (int i0 = 0; i0 < T; i0 += kAbTile) {
+      const int mb = j0 - (i0 + kAbTile - 1) + T - 1;         // table row of (first key of the CTA, last query of the tile)
+      __syncthreads();
+      stage_rows_biased(Qu, qb, D, i0, kAbTile, 0, T, u + h * 64);
+      stage_rows_biased(Qv, qb, D, i0, kAbTile, 0, T, vb + h * 64);
+      stage_rows(Dc, db_, D, i0, kAbTile, 0, T);
+      stage_rows(Ps, pb, D, mb, kAbBand, 0, R);
+      if (threadIdx.x < kAbTile) {
+        const int ii = i0 + threadIdx.x;
+        ls[threadIdx.x] = ii < T ? lrow[ii] : INFINITY;
+        ds[threadIdx.x] = ii < T ? drow[ii] : 0.f;
+      }
+      __syncthreads();
+      const int i = i0 + lane;
+      if (active && i < T) {
+        const float* qur = Qu + lane * kAbPitch;
+        const float* dr = Dc + lane * kAbPitch;
+        const float s = 0.125f * (sdot64(kj, qur) + sdot64(Ps + (j - i + T - 1 - mb) * kAbPitch, Qv + lane * kAbPitch));
+        const float a = __expf(s - ls[lane]);
+        const float g = a * (sdot64(vj, dr) - ds[lane]) * 0.125f;
+        saxpy64(av, a, dr);
+        saxpy64(ak, g, qur);
+      }
     }
   }
+  if (j >= T) return;
   const float2 rk = reduce64(ak, lane), rv = reduce64(av, lane);
   dk[ko + lane] = rk.x; dk[ko + lane + 32] = rk.y;
   dv[ko + lane] = rv.x; dv[ko + lane + 32] = rv.y;
@@ -190,21 +236,28 @@ __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_pos_kernel(
     const float* __restrict__ u, const float* __restrict__ vb, const int32_t* __restrict__ lengths,
     const float* __restrict__ dctx, const float* __restrict__ lse, const float* __restrict__ delta,
     float* __restrict__ dp, int B, int T, int H) {
-  __shared__ __align__(16) float sm[kAbWarps][3][64];
+  extern __shared__ __align__(16) float pos_smem[];            // kPosSmemBytes (> 48 KB: opt-in, set by the launcher)
+  float* Qu = pos_smem;
+  float* Qv = Qu + kAbTile * kAbPitch;
+  float* Dc = Qv + kAbTile * kAbPitch;
+  float* Kb = Dc + kAbTile * kAbPitch;
+  float* Vb = Kb + kAbBand * kAbPitch;
+  float (*vec)[64] = reinterpret_cast<float (*)[64]>(Vb + kAbBand * kAbPitch);
+  float* ls = &vec[kAbWarps][0];
+  float* ds = ls + kAbTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * kAbWarps + warp, h = blockIdx.y;
+  const int m0 = blockIdx.x * kAbWarps, m = m0 + warp, h = blockIdx.y;
   const int R = 2 * T - 1;
-  if (m >= R) return;
+  const bool active = m < R;
   const int D = H * kHeadDim;
-  float* pm = sm[warp][0];
-  float* su = sm[warp][1];
-  float* sv = sm[warp][2];
-  for (int d = lane; d < 64; d += 32) { pm[d] = p[(long)m * D + h * 64 + d]; su[d] = u[h * 64 + d]; sv[d] = vb[h * 64 + d]; }
-  __syncwarp();
+  float* pm = vec[warp];
+  if (active)
+    for (int d = lane; d < 64; d += 32) pm[d] = p[(long)m * D + h * 64 + d];
   float ap[64];
 #pragma unroll
   for (int d = 0; d < 64; ++d) ap[d] = 0.f;
-  const int shift = m - (T - 1);                  // j = i + shift
+  const int shift = m - (T - 1);                   // this warp's key for query i is j = i + shift
+  const int shift0 = m0 - (T - 1);                 // the CTA's first table row
   for (int b = 0; b < B; ++b) {
     int L = T;
     if (lengths) { L = lengths[b]; L = L < 0 ? 0 : (L > T ? T : L); }
@@ -214,32 +267,36 @@ __global__ void __launch_bounds__(32 * kAbWarps) attn_bwd_pos_kernel(
     const float* db_ = dctx + (long)b * T * D + h * kHeadDim;
     const float* lrow = lse + ((long)b * H + h) * T;
     const float* drow = delta + ((long)b * H + h) * T;
-    const int ilo = shift < 0 ? -shift : 0;       // j >= 0
-    int ihi = L - shift;                          // j < L
+    // queries that have a valid key under ANY of the CTA's table rows: 0 <= i + shift0 + w < L for some w in [0, 8)
+    int ilo = -(shift0 + kAbWarps - 1);
+    if (ilo < 0) ilo = 0;
+    int ihi = L - shift0;
     if (ihi > T) ihi = T;
-    for (int i0 = ilo; i0 < ihi; i0 += 32) {
-      const int i = i0 + lane;
-      if (i < ihi) {
-        const int j = i + shift;
-        const float* qr = qb + (long)i * D;
-        const float s = 0.125f * (dot64_biased(qr, su, kb + (long)j * D) + dot64_biased(qr, sv, pm));
-        const float a = __expf(s - lrow[i]);
-        float da = 0.f;
-        {
-          const float* dr = db_ + (long)i * D;
-          const float* vr = vbase + (long)j * D;
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const float4 x = reinterpret_cast<const float4*>(dr)[t];
-            const float4 y = reinterpret_cast<const float4*>(vr)[t];
-            da = fmaf(x.x, y.x, da); da = fmaf(x.y, y.y, da); da = fmaf(x.z, y.z, da); da = fmaf(x.w, y.w, da);
-          }
-        }
-        const float gg = a * (da - drow[i]) * 0.125f;
-        axpy64(ap, gg, qr, sv);
+    for (int i0 = ilo; i0 < ihi; i0 += kAbTile) {
+      const int jb = i0 + shift0;                  // key of (first query of the tile, first table row of the CTA)
+      __syncthreads();
+      stage_rows_biased(Qu, qb, D, i0, kAbTile, 0, T, u + h * 64);
+      stage_rows_biased(Qv, qb, D, i0, kAbTile, 0, T, vb + h * 64);
+      stage_rows(Dc, db_, D, i0, kAbTile, 0, T);
+      stage_rows(Kb, kb, D, jb, kAbBand, 0, L);
+      stage_rows(Vb, vbase, D, jb, kAbBand, 0, L);
+      if (threadIdx.x < kAbTile) {
+        const int ii = i0 + threadIdx.x;
+        ls[threadIdx.x] = ii < T ? lrow[ii] : INFINITY;
+        ds[threadIdx.x] = ii < T ? drow[ii] : 0.f;
+      }
+      __syncthreads();
+      const int i = i0 + lane, j = i + shift;
+      if (active && i < T && j >= 0 && j < L) {
+        const float* qvr = Qv + lane * kAbPitch;
+        const float s = 0.125f * (sdot64(Qu + lane * kAbPitch, Kb + (j - jb) * kAbPitch) + sdot64(pm, qvr));
+        const float a = __expf(s - ls[lane]);
+        const float g = a * (sdot64(Dc + lane * kAbPitch, Vb + (j - jb) * kAbPitch) - ds[lane]) * 0.125f;
+        saxpy64(ap, g, qvr);
       }
     }
   }
+  if (!active) return;
   const float2 rp = reduce64(ap, lane);
   dp[(long)m * D + h * 64 + lane] = rp.x;
   dp[(long)m * D + h * 64 + lane + 32] = rp.y;
@@ -277,7 +334,10 @@ int avsr_relpos_attention_bwd(const float* q, const float* k, const float* v, co
   attn_bwd_keys_kernel<<<dim3(cdiv(T, kAbWarps), H, B), block, 0, st>>>(q, k, v, p, pos_bias_u, pos_bias_v, lengths, dctx, lse, delta,
                                                                          dk, dv, T, H);
   AVSR_CHECK_LAUNCH();
-  attn_bwd_pos_kernel<<<dim3(cdiv(2 * T - 1, kAbWarps), H), block, 0, st>>>(q, k, v, p, pos_bias_u, pos_bias_v, lengths, dctx, lse,
+  static const cudaError_t pos_attr =
+      cudaFuncSetAttribute(attn_bwd_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPosSmemBytes);
+  AVSR_REQUIRE(pos_attr == cudaSuccess, "attention backward: shared memory opt-in failed");
+  attn_bwd_pos_kernel<<<dim3(cdiv(2 * T - 1, kAbWarps), H), block, kPosSmemBytes, st>>>(q, k, v, p, pos_bias_u, pos_bias_v, lengths, dctx, lse,
                                                                              delta, dp, B, T, H);
   AVSR_CHECK_LAUNCH();
   return AVSR_OK;

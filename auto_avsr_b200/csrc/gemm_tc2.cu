@@ -96,6 +96,16 @@ struct T2Cfg {
   __host__ __device__ static constexpr int sub_brow(int j) { return j == 0 ? 0 : kN0 / 2; }     // first B smem row
 };
 
+// -DAVSR_TRACE_EPI (with -DAVSR_TRACE): marks 2..5 and 9 are taken by the first epilogue warp instead of the producer / MMA
+// warps: 2 first chunk in registers, 3 first chunk staged, 4 first store issued, 5 last store issued, 9 reserved
+#if defined(AVSR_TRACE) && defined(AVSR_TRACE_EPI)
+#define T2_PMARK(cond, s) do { } while (0)
+#define T2_EMARK(s) AVSR_TRACE_MARK(threadIdx.x == 64, trc, s)
+#else
+#define T2_PMARK(cond, s) AVSR_TRACE_MARK(cond, trc, s)
+#define T2_EMARK(s) do { } while (0)
+#endif
+
 // RELU / RESID are compile-time: a predicated-off instruction still takes an issue slot, and this epilogue is not
 // overlapped with anything (one tile per cluster).
 // PREB (default inside the encoder forward, AVSR_B200_PREB=0 disables; prepared weights only; +0.6 % r02 A/B): the B operand (weights) does not depend on the
@@ -200,7 +210,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (kb < S) {                                                   // expect_tx + B already issued before the wait
           if (elect_one_sync())
             tma_load_2d_2sm(base + s * Cfg::kStageBytes, &tmA, (kb0 + kb) * KE, m0 + (int)rank * 128, full_bar(s));
-          AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 2);
+          T2_PMARK(kb == 0 && lane == 0, 2);
           continue;
         }
       }
@@ -216,9 +226,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_2d_2sm(dst + Cfg::kABytes + Cfg::sub_brow(1) * 128, &tmB1, kc,
                           n0 + Cfg::kN0 + (int)rank * (Cfg::kN1 / 2), full_bar(s));
       }
-      AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 2);
+      T2_PMARK(kb == 0 && lane == 0, 2);
     }
-    AVSR_TRACE_MARK(lane == 0, trc, 3);
+    T2_PMARK(lane == 0, 3);
   } else if (warp == 1) {
     if (rank == 0) {
       constexpr uint32_t idesc0 = umma_idesc_f16(256, Cfg::kN0);
@@ -228,7 +238,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        AVSR_TRACE_MARK(kb == 0 && lane == 0, trc, 4);
+        T2_PMARK(kb == 0 && lane == 0, 4);
         const uint32_t a_addr = base + s * Cfg::kStageBytes;
         const uint64_t a_desc = umma_desc_sw128(a_addr);
         if (elect_one_sync()) {
@@ -243,7 +253,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (kb == nkb - 1) tc_commit_2sm(tmem_full_bar);   // accumulator complete: wakes both CTAs' epilogues
         }
       }
-      AVSR_TRACE_MARK(lane == 0, trc, 5);
+      T2_PMARK(lane == 0, 5);
     }
   } else {
     // ---------------------------------------------------------------- epilogue (both CTAs: own 128 rows)
@@ -407,6 +417,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ sw) << 4));
           tmem_ld_wait();
+          if (c == cb) T2_EMARK(2);
           const float* sb = s_bias + c;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -416,10 +427,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           fence_proxy_async();
           __syncwarp();
+          if (c == cb) T2_EMARK(3);
           if (elect_one_sync()) {
             tma_store_3d(&tmOut, res_base + (c >> 5) * (128 * 128) + q * 4096, n0 + c, mrow, split);
             tma_store_commit();
           }
+          if (c == cb) T2_EMARK(4);
+          if (c + 32 >= ce) T2_EMARK(5);
         }
       } else {
         // staging: two 4 KB boxes per warp in the (now idle) pipeline stages
@@ -467,6 +481,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float* v = (ci & 1) ? vb : va;
         float* vn = (ci & 1) ? va : vb;
         tmem_ld_wait();
+        if (ci == 0) T2_EMARK(2);
         if (ci + 1 < NC) {
           tmem_ld32(trow + c + 64, vn);
           tmem_ld32(trow + c + 96, vn + 32);
@@ -490,10 +505,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         fence_proxy_async();
         __syncwarp();
+        if (ci == 0) T2_EMARK(3);
         if (elect_one_sync()) {
           tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 1) * 4096u, n0 + c, mrow, split);
           tma_store_commit();
         }
+        if (ci == 0) T2_EMARK(4);
+        if (ci == NC - 1) T2_EMARK(5);
       }
       if (elect_one_sync()) tma_store_wait_read_n<0>();
     }

@@ -21,7 +21,7 @@ def main() -> None:
 
     def one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + g.NVCC_FLAGS + ["-DAVSR_TRACE", "-c", os.path.join(g.CSRC, src), "-o", obj]
+        cmd = [nvcc] + g.NVCC_FLAGS + ["-DAVSR_TRACE"] + (["-DAVSR_TRACE_EPI"] if os.environ.get("AVSR_TRACE_EPI") else []) + ["-c", os.path.join(g.CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise SystemExit(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -26,6 +26,9 @@ from auto_avsr_b200.synthetic import SHAPES, encoder_input, encoder_state_dict  
 
 WORDS = 16
 GEMM_MARKS = ["prologue", "dep-wait", "1st TMA", "TMA issue", "1st full", "main loop", "acc visible", "epilogue", "drain"]
+if os.environ.get("AVSR_TRACE_EPI"):      # trace library built with AVSR_TRACE_EPI=1: slots 2..5 belong to the first epilogue warp
+    GEMM_MARKS = ["prologue", "dep-wait", "chunk0 in regs", "chunk0 staged", "store0 issued", "last store issued",
+                  "acc visible", "epilogue", "drain"]
 ATT_MARKS = ["prologue", "dep-wait", "1st S/G issue", "S/G(0) ready", "softmax(0)", "P.V(0)", "rest of tiles", "drain"]
 EPI = {0: "linear", 1: "qkv", 2: "vt", 3: "glu", 4: "pos"}
 
