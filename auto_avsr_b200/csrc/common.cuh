@@ -151,6 +151,12 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// the same with ReLU folded into the conversion (F2FP.SATFINITE.RELU): negative -> +0, NaN stays NaN like torch.relu
+__device__ __forceinline__ uint32_t pack_half2_sat_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 // store 4 consecutive operand values (dst 16-byte aligned for float, 8-byte aligned for half)
 template <typename TOp>
 __device__ __forceinline__ void store_op4(TOp* dst, float a, float b, float c, float d);

@@ -33,6 +33,29 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Relaxed: what the arrival
+// publishes is tensor-memory state, ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync on this side and
+// tcgen05.fence::after_thread_sync on the waiter's; a release at cluster scope costs a MEMBAR.ALL.GPU per arrival
+// (r02 trace: the first MMA of the 384-wide tile started 1400 cycles late behind 16 of them).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {  // one warp in EACH CTA of the pair, same dst offset
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
@@ -90,7 +113,7 @@ struct T2Cfg {
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = BNP <= 128 ? 128 : (BNP <= 256 ? 256 : 512);
   static_assert(kStages >= 2 && BNP % 32 == 0 && BNP <= 512, "bad pair tile");
-  static_assert(MODE != EPI_LINEAR || kStages * kStageBytes >= 8 * 8192, "LINEAR staging (8 warps x 2 x 4 KB) lives in the stages");
+  static_assert(MODE != EPI_LINEAR || kStages * kStageBytes >= 8 * 16384, "LINEAR staging (8 warps x 4 x 4 KB) lives in the stages");
   __host__ __device__ static constexpr int sub_n(int j) { return j == 0 ? kN0 : kN1; }
   __host__ __device__ static constexpr int sub_col(int j) { return j == 0 ? 0 : kN0; }          // first tile column
   __host__ __device__ static constexpr int sub_brow(int j) { return j == 0 ? 0 : kN0 / 2; }     // first B smem row
@@ -129,6 +152,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bars = base + kBarOff;   // full[S], empty[S], tmem_full, (tmem slot), res_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kBarOff + (2 * S + 1) * 8);
   const uint32_t res_full_bar = bars + 8u * (2 * S + 2);
+  const uint32_t acc_ready_bar = bars + 8u * (2 * S + 3);   // leader's: the 16 epilogue warps of the pair pre-filled the accumulator
   float* s_bias = reinterpret_cast<float*>(gen + kBarOff + 256);
   uint8_t* stg_base = gen + kBarOff + 256 + Cfg::kVecBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -152,6 +176,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kb0 = split * nkb;
 
   pdl_launch_dependents();
+  // PREB: the per-column vectors are fetched into registers now, so that their latency is spent under the prologue's
+  // barrier set-up / TMEM allocation / cluster sync instead of in front of the accumulator pre-fill
+  const bool has_bias = ep.bias != nullptr;
+  constexpr int kVecPer = (BNP + (T2_THREADS - 64) - 1) / (T2_THREADS - 64);
+  float vpre[MODE == EPI_QK ? 3 : 1][kVecPer];
+  auto fetch_vectors = [&]() {
+#pragma unroll
+    for (int i = 0; i < kVecPer; ++i) {
+      const int c = (int)threadIdx.x - 64 + i * (T2_THREADS - 64);
+      const int n = n0 + c;
+      vpre[0][i] = (has_bias && c < BNP && n < ep.N) ? ep.bias[n] : 0.f;
+      if constexpr (MODE == EPI_QK) {
+        const bool isq = c < BNP && n < ep.H * kHeadDim;
+        vpre[1][i] = isq ? ep.pos_u[n] : 0.f;
+        vpre[2][i] = isq ? ep.pos_v[n] : 0.f;
+      }
+    }
+  };
+  if constexpr (PREB) {
+    if (warp >= 2) fetch_vectors();
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -159,6 +204,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     mbar_init(res_full_bar, 1);
+    mbar_init(acc_ready_bar, 16);
     if constexpr (MODE == EPI_LINEAR) { tma_prefetch_desc(&tmOut); if (RESID) tma_prefetch_desc(&tmRes); }
     fence_barrier_init();
   }
@@ -172,6 +218,47 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // Producer and MMA warps run warp-uniform loops and guard only the instruction issue with elect.sync: TMA / tcgen05
   // operands live in uniform registers, and inside a divergent `lane == 0` region every operand is rebuilt and moved
   // per instruction (r02 SASS: ~22 instructions + an ELECT / BRA.U.ANY loop per UTCHMMA).
+  // The bias is not added in the epilogue: the epilogue warps, idle until the accumulator is complete, write it into the
+  // accumulator (TMEM column c of every row = bias[n0 + c]) while the pipeline fills, and the MMAs accumulate on top --
+  // r02 epilogue trace: 206 instructions per 64-column chunk, 64 of them the bias FADDs behind 16 dependent LDS.128.
+  auto stage_vectors_and_prefill = [&]() {
+    if constexpr (!PREB) fetch_vectors();
+#pragma unroll
+    for (int i = 0; i < kVecPer; ++i) {
+      const int c = (int)threadIdx.x - 64 + i * (T2_THREADS - 64);
+      if (c < BNP) {
+        s_bias[c] = vpre[0][i];
+        if constexpr (MODE == EPI_QK) {
+          s_bias[BNP + c] = vpre[1][i];
+          s_bias[2 * BNP + c] = vpre[2][i];
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (has_bias) {
+      const int q = warp & 3, chalf = (warp - 2) >> 2;
+      const int cb = (BNP == 96) ? chalf * 64 : chalf * (BNP / 2);
+      const int ce = (BNP == 96) ? (chalf ? 96 : 64) : cb + BNP / 2;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = cb; c < ce; c += 32) {
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(s_bias + c + 4 * j);
+          bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+        }
+        tmem_st32(trow + c, bv);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one_sync()) mbar_arrive_cluster(acc_ready_bar, 0);
+    }
+  };
+  if constexpr (PREB) {          // prepared weights: the bias does not depend on the predecessor either
+    if (warp >= 2) stage_vectors_and_prefill();
+  }
   if constexpr (PREB) {
     if (warp == 0) {
       const int npre = nkb < S ? nkb : S;      // every stage is free on entry: no empty-barrier wait needed
@@ -191,6 +278,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_wait();
   AVSR_TRACE_MARK(threadIdx.x == 0, trc, 1);
   AVSR_TRACE_STAMP(threadIdx.x == 0, trc, 10);
+  if constexpr (!PREB) {
+    if (warp >= 2) stage_vectors_and_prefill();
+  }
 
   if (warp == 0) {
     if constexpr (RESID) {
@@ -233,6 +323,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (rank == 0) {
       constexpr uint32_t idesc0 = umma_idesc_f16(256, Cfg::kN0);
       constexpr uint32_t idesc1 = umma_idesc_f16(256, Cfg::kNSub == 2 ? Cfg::kN1 : Cfg::kN0);
+      const uint32_t acc0 = has_bias ? 1u : 0u;          // pre-filled accumulator: the first MMA accumulates too
+      if (has_bias) {
+        mbar_wait_cluster(acc_ready_bar, 0);
+        tc_fence_after();
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (kb / S) & 1;
@@ -247,7 +342,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + Cfg::sub_brow(j) * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              mma_f16_2sm(tmem_base + Cfg::sub_col(j), a_desc + 2 * k, b_desc + 2 * k, j == 0 ? idesc0 : idesc1, (kb | k) != 0);
+              mma_f16_2sm(tmem_base + Cfg::sub_col(j), a_desc + 2 * k, b_desc + 2 * k, j == 0 ? idesc0 : idesc1, acc0 | (uint32_t)((kb | k) != 0));
           }
           tc_commit_2sm(empty_bar(s));       // frees the stage in both CTAs
           if (kb == nkb - 1) tc_commit_2sm(tmem_full_bar);   // accumulator complete: wakes both CTAs' epilogues
@@ -264,16 +359,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cb = (BNP == 96) ? chalf * 64 : chalf * (BNP / 2);
     const int ce = (BNP == 96) ? (chalf ? 96 : 64) : cb + BNP / 2;
     const int pr = lane >> 3, pc = lane & 7;
-    for (int c = threadIdx.x - 64; c < BNP; c += T2_THREADS - 64) {
-      const int n = n0 + c;
-      s_bias[c] = (ep.bias && n < ep.N) ? ep.bias[n] : 0.f;
-      if constexpr (MODE == EPI_QK) {
-        const bool isq = n < ep.H * kHeadDim;
-        s_bias[BNP + c] = isq ? ep.pos_u[n] : 0.f;
-        s_bias[2 * BNP + c] = isq ? ep.pos_v[n] : 0.f;
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     AVSR_TRACE_MARK(threadIdx.x == 64, trc, 6);
@@ -288,9 +373,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld32(trow + c, val);
         tmem_ld32(trow + c + 64, gate);
         tmem_ld_wait();
-        const float* sb = s_bias + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = (val[j] + sb[j]) * sigmoidf_fast(gate[j] + sb[64 + j]);
+        for (int j = 0; j < 32; ++j) val[j] *= sigmoidf_fast(gate[j]);
         stage_write_f32(stg, lane, val, false);
         __syncwarp();
 #pragma unroll
@@ -306,9 +390,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld32(trow + c + 32, v + 32);
         tmem_ld_wait();
         const int n = n0 + c;
-        const float* sb = s_bias + c;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += sb[j];
         const int np = n + pc * 8;
         const int seg = np / D, nn = np - seg * D;
         const int hh = nn >> 6, d0 = nn & 63;
@@ -339,7 +420,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_wait();
           const float* sv = s_bias + 2 * BNP + c;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] += sb[j] + sv[j];
+          for (int j = 0; j < 64; ++j) v[j] += sv[j];
           stage_write_f16(stg, lane, v);
           __syncwarp();
 #pragma unroll
@@ -365,9 +446,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        const float* sb = s_bias + c;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += sb[j];
         const int nb = n0 + c;
         if (nb < ep.n_valid) {
           const int nv = ep.n_valid - nb;                  // valid columns of this chunk (>= 32: all)
@@ -418,11 +496,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 8; ++j) r[j] = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ sw) << 4));
           tmem_ld_wait();
           if (c == cb) T2_EMARK(2);
-          const float* sb = s_bias + c;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            r[j].x = fmaf(ep.alpha, v[4 * j] + sb[4 * j], r[j].x); r[j].y = fmaf(ep.alpha, v[4 * j + 1] + sb[4 * j + 1], r[j].y);
-            r[j].z = fmaf(ep.alpha, v[4 * j + 2] + sb[4 * j + 2], r[j].z); r[j].w = fmaf(ep.alpha, v[4 * j + 3] + sb[4 * j + 3], r[j].w);
+            r[j].x = fmaf(ep.alpha, v[4 * j], r[j].x); r[j].y = fmaf(ep.alpha, v[4 * j + 1], r[j].y);
+            r[j].z = fmaf(ep.alpha, v[4 * j + 2], r[j].z); r[j].w = fmaf(ep.alpha, v[4 * j + 3], r[j].w);
             *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ sw) << 4)) = r[j];
           }
           fence_proxy_async();
@@ -436,30 +513,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (c + 32 >= ce) T2_EMARK(5);
         }
       } else {
-        // staging: two 4 KB boxes per warp in the (now idle) pipeline stages
-        const uint32_t stg0 = base + (uint32_t)(warp - 2) * 8192u;
+        // staging: a ring of four 4 KB boxes per warp in the (now idle) pipeline stages -- the export, not the
+        // conversion, bounds this epilogue (r02 trace), so the stores are queued as early as the data exists
+        const uint32_t stg0 = base + (uint32_t)(warp - 2) * 16384u;
 #pragma unroll 1
         for (int c = cb, ci = 0; c < ce; c += 32, ++ci) {
           float v[32];
           tmem_ld32(trow + c, v);
-          if (ci >= 2) {                                   // the box is free once its previous store has been read
-            if (elect_one_sync()) tma_store_wait_read_n<1>();
+          if (ci >= 4) {                                   // the box is free once its previous store has been read
+            if (elect_one_sync()) tma_store_wait_read_n<3>();
             __syncwarp();
           }
           tmem_ld_wait();
-          const float* sb = s_bias + c;
-          uint8_t* box = gen + (warp - 2) * 8192 + (ci & 1) * 4096;
+          uint8_t* box = gen + (warp - 2) * 16384 + (ci & 3) * 4096;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j] + sb[4 * j], v[4 * j + 1] + sb[4 * j + 1], v[4 * j + 2] + sb[4 * j + 2],
-                                   v[4 * j + 3] + sb[4 * j + 3]);
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ sw) << 4)) = o;
           }
           fence_proxy_async();
           __syncwarp();
           if (elect_one_sync()) {
-            tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 1) * 4096u, n0 + c, mrow, split);
+            tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 3) * 4096u, n0 + c, mrow, split);
             tma_store_commit();
           }
         }
@@ -471,7 +547,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr int NC = (BNP / 2) / 64;                   // 64-column chunks per warp (4 for the 256x512 pair tile)
       const int mrow = m0 + (int)rank * 128 + q * 32;
       const uint32_t sw = (uint32_t)(lane & 7);
-      const uint32_t stg0 = base + (uint32_t)(warp - 2) * 8192u;
+      const uint32_t stg0 = base + (uint32_t)(warp - 2) * 16384u;
+      static_assert(NC <= 4, "one staging box per chunk");
       float va[64], vb[64];
       tmem_ld32(trow + cb, va);
       tmem_ld32(trow + cb + 32, va + 32);
@@ -486,20 +563,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld32(trow + c + 64, vn);
           tmem_ld32(trow + c + 96, vn + 32);
         }
-        if (ci >= 2) {
-          if (elect_one_sync()) tma_store_wait_read_n<1>();
-          __syncwarp();
-        }
-        const float* sb = s_bias + c;
-        uint8_t* box = gen + (warp - 2) * 8192 + (ci & 1) * 4096;
+        uint8_t* box = gen + (warp - 2) * 16384 + ci * 4096;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float a = v[8 * j + 2 * e] + sb[8 * j + 2 * e], b = v[8 * j + 2 * e + 1] + sb[8 * j + 2 * e + 1];
-            if (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            pk[e] = pack_half2_sat(a, b);
+            const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+            pk[e] = RELU ? pack_half2_sat_relu(a, b) : pack_half2_sat(a, b);
           }
           *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -507,7 +578,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (ci == 0) T2_EMARK(3);
         if (elect_one_sync()) {
-          tma_store_3d(&tmOut, stg0 + (uint32_t)(ci & 1) * 4096u, n0 + c, mrow, split);
+          tma_store_3d(&tmOut, stg0 + (uint32_t)ci * 4096u, n0 + c, mrow, split);
           tma_store_commit();
         }
         if (ci == 0) T2_EMARK(4);
