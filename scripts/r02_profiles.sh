@@ -2,7 +2,7 @@
 # ncu evidence of round 2 (run under gpurun, one GPU): the launch list of one forward (direct launches, f16 path) and a
 # --set full capture of every kernel kind of a layer.  Summaries are made here, copied to profiles/ in the build container.
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --log-file gpurun_out/r02_launches_f16.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 405 -c 180 --csv --log-file gpurun_out/r02_launches_f16.csv \
     python scripts/profile_launches.py 2 f16 > gpurun_out/r02_launches.log 2>&1
 python scripts/summarize_launches.py gpurun_out/r02_launches_f16.csv > gpurun_out/r02_launches_f16.summary.txt 2>&1
 ncu --set full --clock-control none --import-source on \
