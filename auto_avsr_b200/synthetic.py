@@ -113,6 +113,43 @@ def frontend_features(lengths: Sequence[int], idim: int = 512, seed: int = 4321,
     return encoder_input(lengths, idim, seed, dtype)
 
 
+def decoder_state_dict(seed: int = 0, odim: int = 5049, d_model: int = 768, n_heads: int = 12, linear_units: int = 3072,
+                       num_blocks: int = 6, dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
+    """Synthetic ``TransformerDecoder.state_dict()`` in the reference's key order
+    (espnet/nets/pytorch_backend/decoder/transformer_decoder.py:159-229; 26 keys per ``DecoderLayer`` + ``embed.0``,
+    ``after_norm``, ``output_layer``).  As for the encoder every LayerNorm affine and bias is non-trivial."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def uni(key, shape, bound):
+        sd[key] = (torch.rand(shape, generator=_gen(seed, key), dtype=torch.float64) * 2 - 1).mul_(bound).to(dtype)
+
+    def nrm(key, shape, std):
+        sd[key] = (torch.randn(shape, generator=_gen(seed, key), dtype=torch.float64) * std).to(dtype)
+
+    def linear(pfx, out_f, in_f):
+        uni(pfx + ".weight", (out_f, in_f), 1.0 / math.sqrt(in_f))
+        nrm(pfx + ".bias", (out_f,), 0.1)
+
+    def lnorm(pfx):
+        sd[pfx + ".weight"] = (torch.rand((d_model,), generator=_gen(seed, pfx + ".weight"), dtype=torch.float64) + 0.5).to(dtype)
+        nrm(pfx + ".bias", (d_model,), 0.1)
+
+    nrm("embed.0.weight", (odim, d_model), 1.0 / math.sqrt(d_model))      # x sqrt(d) in PositionalEncoding -> O(1) rows
+    for l in range(num_blocks):
+        p = f"decoders.{l}."
+        for att in ("self_attn", "src_attn"):
+            for lin in ("linear_q", "linear_k", "linear_v", "linear_out"):
+                linear(p + att + "." + lin, d_model, d_model)
+        linear(p + "feed_forward.w_1", linear_units, d_model)
+        linear(p + "feed_forward.w_2", d_model, linear_units)
+        lnorm(p + "norm1")
+        lnorm(p + "norm2")
+        lnorm(p + "norm3")
+    lnorm("after_norm")
+    linear("output_layer", odim, d_model)
+    return sd
+
+
 #: Canonical length sets of SURVEY.md §8 (25 Hz frames).
 SHAPES: Dict[str, Sequence[int]] = {
     "S1": [100],

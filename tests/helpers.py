@@ -53,3 +53,20 @@ def record(test, case, observed, bound):
             f.write(json.dumps(line) + "\n")
     except OSError:
         pass
+
+
+def load_decoder_case(name):
+    """Golden case of the attention-decoder scoring path (oracle/make_golden_decoder.py): config, the regenerated
+    decoder / CTC weights, the (T, d) memory and the fixed prefixes of every stored step."""
+    from auto_avsr_b200.synthetic import decoder_state_dict
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = {k[4:]: int(z[k]) for k in z.files if k.startswith("cfg_")}
+    dec_sd = decoder_state_dict(cfg["wseed"], cfg["odim"], cfg["d_model"], cfg["n_heads"], cfg["linear_units"],
+                                cfg["num_blocks"])
+    head_sd = head_state_dict(cfg["wseed"], 64, cfg["d_model"], cfg["odim"])
+    memory = encoder_input([cfg["T"]], cfg["d_model"], cfg["xseed"])[0]
+    g = torch.Generator().manual_seed(cfg["xseed"] * 7 + 1)
+    body = torch.randint(1, cfg["odim"] - 1, (cfg["n_hyp"], cfg["steps"]), generator=g)
+    sos = torch.full((cfg["n_hyp"], 1), cfg["odim"] - 1, dtype=torch.long)
+    prefixes = [torch.cat([sos, body[:, :s]], dim=1) for s in range(cfg["steps"] + 1)]
+    return dict(z=z, cfg=cfg, dec_sd=dec_sd, head_sd=head_sd, memory=memory, prefixes=prefixes)
