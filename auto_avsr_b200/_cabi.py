@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AVSR_B200_LIB") or os.path.join(_HERE, "csrc", "libav
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class AvsrError(RuntimeError):
@@ -54,9 +54,37 @@ class LayerParams(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _ in LAYER_FIELDS]
 
 
+class DecoderConfig(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_heads", C.c_int32), ("linear_units", C.c_int32),
+                ("num_blocks", C.c_int32), ("odim", C.c_int32)]
+
+
+#: field order of AvsrDecoderLayerParams (include/avsr_b200.h) -> reference state-dict key suffix
+DECODER_LAYER_FIELDS = [
+    ("self_q_w", "self_attn.linear_q.weight"), ("self_q_b", "self_attn.linear_q.bias"),
+    ("self_k_w", "self_attn.linear_k.weight"), ("self_k_b", "self_attn.linear_k.bias"),
+    ("self_v_w", "self_attn.linear_v.weight"), ("self_v_b", "self_attn.linear_v.bias"),
+    ("self_out_w", "self_attn.linear_out.weight"), ("self_out_b", "self_attn.linear_out.bias"),
+    ("src_q_w", "src_attn.linear_q.weight"), ("src_q_b", "src_attn.linear_q.bias"),
+    ("src_k_w", "src_attn.linear_k.weight"), ("src_k_b", "src_attn.linear_k.bias"),
+    ("src_v_w", "src_attn.linear_v.weight"), ("src_v_b", "src_attn.linear_v.bias"),
+    ("src_out_w", "src_attn.linear_out.weight"), ("src_out_b", "src_attn.linear_out.bias"),
+    ("ff_w1", "feed_forward.w_1.weight"), ("ff_b1", "feed_forward.w_1.bias"),
+    ("ff_w2", "feed_forward.w_2.weight"), ("ff_b2", "feed_forward.w_2.bias"),
+    ("norm1_w", "norm1.weight"), ("norm1_b", "norm1.bias"),
+    ("norm2_w", "norm2.weight"), ("norm2_b", "norm2.bias"),
+    ("norm3_w", "norm3.weight"), ("norm3_b", "norm3.bias"),
+]
+
+
+class DecoderLayerParams(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _ in DECODER_LAYER_FIELDS]
+
+
 #: every symbol include/avsr_b200.h declares: name -> (restype, argtypes)
 _P, _I, _Z, _F = C.c_void_p, C.c_int, C.c_size_t, C.c_float
 _CFG = C.POINTER(EncoderConfig)
+_DCFG = C.POINTER(DecoderConfig)
 SIGNATURES = {
     "avsr_abi_version": (_I, []),
     "avsr_last_error": (C.c_char_p, []),
@@ -107,6 +135,15 @@ SIGNATURES = {
     "avsr_proj_encoder": (_I, [_CFG, _P, _P, _I, _I, _I, _P, _P, _Z, _I, _P]),
     "avsr_ctc_workspace_bytes": (_Z, [_CFG, _I, _I]),
     "avsr_ctc_logprobs": (_I, [_CFG, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _I, _P]),
+    "avsr_decoder_prepared_bytes": (_Z, [_DCFG]),
+    "avsr_prepare_decoder": (_I, [_DCFG, C.POINTER(DecoderLayerParams), _P, _P, _P, _P, _P, _P, _Z, _I, _P]),
+    "avsr_decoder_session_bytes": (_Z, [_DCFG, _I, _I, _I]),
+    "avsr_decoder_begin": (_I, [_DCFG, _P, _P, _I, _I, _I, _P, _Z, _I, _P]),
+    "avsr_decoder_step_workspace_bytes": (_Z, [_DCFG, _I, _I, _I]),
+    "avsr_decoder_step": (_I, [_DCFG, _P, _P, _Z, _I, _I, _I, _P, _P, _I, _I, _P, _P, _Z, _I, _P]),
+    "avsr_ctc_prefix_init": (_I, [_P, _I, _I, _I, _P, _P]),
+    "avsr_ctc_prefix_score": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "avsr_ctc_prefix_select": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }
 
 if not os.path.exists(LIB_PATH):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVSR_ABI_VERSION 9
+#define AVSR_ABI_VERSION 10
 
 enum {
   AVSR_OK = 0,
@@ -286,6 +286,75 @@ int avsr_relpos_attention_bwd(const float *q, const float *k, const float *v, co
 int avsr_pack_padded(const float *flat, const int64_t *offsets, float *out, int32_t *lengths_out, int B, int Tmax, int d,
                      float pad_value, void *stream);
 int avsr_unpack_padded(const float *padded, const int64_t *offsets, float *flat, int B, int Tmax, int d, void *stream);
+
+/* ---- attention-decoder scoring path + CTC prefix scorer ----------------------------------------------
+ * What the reference's BatchBeamSearch asks of its two scorers at every step (espnet/nets/batch_beam_search.py:208-285):
+ *   TransformerDecoder.batch_score -> forward_one_step  (espnet/nets/pytorch_backend/decoder/transformer_decoder.py:260-334,
+ *                                                        DecoderLayer.forward :63-140; 6 pre-norm layers, d 768, ff 3072)
+ *   CTCPrefixScorer.batch_score_partial -> CTCPrefixScoreTH.__call__  (espnet/nets/scorers/ctc.py:99-130,
+ *                                                        espnet/nets/ctc_prefix_score.py:72-200)
+ * The reference keeps every layer's OUTPUT per hypothesis and re-projects K/V of the whole prefix and of the whole
+ * encoder memory at every step; here K/V are projected once into a per-utterance SESSION buffer the caller owns:
+ * source-attention K|V of all layers at avsr_decoder_begin, self-attention q|k|v of a position when it is decoded,
+ * addressed (layer, position, beam slot).  A hypothesis is the list of slots of its prefix: re-ordering the beam copies
+ * nothing. */
+typedef struct AvsrDecoderConfig {
+  int32_t d_model;       /* 768 (e2e_asr_conformer.py:41-47) */
+  int32_t n_heads;       /* 12 */
+  int32_t linear_units;  /* 3072 */
+  int32_t num_blocks;    /* 6 (<= 16) */
+  int32_t odim;          /* vocabulary, 5049 */
+} AvsrDecoderConfig;
+
+/* One DecoderLayer's parameters under the reference's names (transformer_decoder.py:36-61): Linear weights (out, in). */
+typedef struct AvsrDecoderLayerParams {
+  const float *self_q_w, *self_q_b, *self_k_w, *self_k_b, *self_v_w, *self_v_b, *self_out_w, *self_out_b;
+  const float *src_q_w, *src_q_b, *src_k_w, *src_k_b, *src_v_w, *src_v_b, *src_out_w, *src_out_b;
+  const float *ff_w1, *ff_b1, *ff_w2, *ff_b2;
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b;
+} AvsrDecoderLayerParams;
+
+/* One-off layout step (after every parameter update): self q|k|v and source k|v weights concatenated, GEMM weights in the
+ * precision's operand storage, output_layer padded to a multiple of 64 rows.  `layers` is a HOST array of num_blocks
+ * structs of DEVICE pointers; embed_w (odim, d) = embed.0.weight, out_w (odim, d) / out_b = output_layer. */
+size_t avsr_decoder_prepared_bytes(const AvsrDecoderConfig *cfg);
+int avsr_prepare_decoder(const AvsrDecoderConfig *cfg, const AvsrDecoderLayerParams *layers, const float *embed_w,
+                         const float *after_norm_w, const float *after_norm_b, const float *out_w, const float *out_b,
+                         void *prepared, size_t prepared_bytes, int precision, void *stream);
+
+/* Utterance start (what batch_init_state + the first batch_score do in the reference): K|V of `memory` (T, d_model) fp32 =
+ * the encoder output, for the source attention of every layer.  The session holds up to max_steps positions x max_hyps
+ * beam slots. */
+size_t avsr_decoder_session_bytes(const AvsrDecoderConfig *cfg, int T, int max_steps, int max_hyps);
+int avsr_decoder_begin(const AvsrDecoderConfig *cfg, const void *prepared, const float *memory, int T, int max_steps,
+                       int max_hyps, void *session, size_t session_bytes, int precision, void *stream);
+
+/* One step of TransformerDecoder.batch_score for n <= max_hyps hypotheses of equal length step + 1:
+ *   tokens (n) int32 DEVICE   the last token of each hypothesis (yseq[:, -1]); hypothesis i occupies beam slot i of
+ *                             position `step`
+ *   anc (step, n) int32 DEVICE  anc[s][i] = beam slot that holds position s < step of hypothesis i's prefix (NULL at step 0)
+ *   logp (n, odim) fp32        log_softmax(output_layer(after_norm(x_last)))  -- transformer_decoder.py:283-289
+ * workspace >= avsr_decoder_step_workspace_bytes. */
+size_t avsr_decoder_step_workspace_bytes(const AvsrDecoderConfig *cfg, int T, int max_steps, int max_hyps);
+int avsr_decoder_step(const AvsrDecoderConfig *cfg, const void *prepared, void *session, size_t session_bytes, int T,
+                      int max_steps, int max_hyps, const int32_t *tokens, const int32_t *anc, int step, int n, float *logp,
+                      void *workspace, size_t workspace_bytes, int precision, void *stream);
+
+/* CTCPrefixScoreTH for ONE utterance (batch 1, no windowing).  logp (T, O) fp32 CTC log-posteriors (ctc.log_softmax);
+ * forward variables use the reference's stacked layouts: r_prev (T, 2, n), r (T, 2, n, S), index 0 = prefix ends in a
+ * non-blank, 1 = in blank; logzero = -1e10.
+ *   avsr_ctc_prefix_init    r0 (T, 2): state of the empty prefix (ctc_prefix_score.py:87-98); its prefix score is 0
+ *   avsr_ctc_prefix_score   one __call__: out_len = tokens after <sos>, last_ids (n) int32, s_prev (n), cand (n, S) int32
+ *                           candidate ids (the pre-beam, unique per row) -> local (n, O) = log_psi - s_prev (logzero off the
+ *                           candidates, <eos> = total prefix probability, blank = logzero), r, log_psi (n, O)
+ *   avsr_ctc_prefix_select  CTCPrefixScorer.select_state for the m kept (parent, token) pairs: r_next (T, 2, m), s_next (m) */
+int avsr_ctc_prefix_init(const float *logp, int T, int O, int blank, float *r0, void *stream);
+int avsr_ctc_prefix_score(const float *logp, int T, int O, int blank, int eos, int out_len, const int32_t *last_ids,
+                          const float *r_prev, const float *s_prev, const int32_t *cand, int n, int S, float *local,
+                          float *r, float *log_psi, void *stream);
+int avsr_ctc_prefix_select(const float *r, const float *log_psi, const int32_t *cand, const int32_t *parent,
+                           const int32_t *token, int T, int O, int n, int S, int m, float *r_next, float *s_next,
+                           void *stream);
 
 #ifdef __cplusplus
 }
