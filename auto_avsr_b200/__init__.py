@@ -9,7 +9,8 @@ CPU or PyTorch fallback.  ``auto_avsr_b200.synthetic`` (weights / inputs generat
 __version__ = "0.1.0"
 
 _LAZY = {"ConformerEncoder", "Encoder", "EncoderLayer", "ConvolutionModule", "RelPositionMultiHeadedAttention",
-         "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "CTC", "ProjEncoder"}
+         "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "CTC", "ProjEncoder", "TransformerDecoder",
+         "CTCPrefixScorer"}
 
 
 def install():
@@ -21,6 +22,13 @@ def install_head(model):
     """Swap an already-built reference ``E2E``'s ``proj_encoder`` and ``ctc`` for the B200 drop-ins (same parameters)."""
     from .install import install_head as _install_head
     return _install_head(model)
+
+
+def install_decoder(model):
+    """Swap an already-built reference ``E2E``'s attention decoder for the B200 scoring drop-in and make
+    ``model.scorers()`` return the B200 CTC prefix scorer (inference / beam search only)."""
+    from .install import install_decoder as _install_decoder
+    return _install_decoder(model)
 
 
 def __getattr__(name):

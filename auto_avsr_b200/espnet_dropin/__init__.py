@@ -6,10 +6,12 @@ from .embedding import RelPositionalEncoding
 from .layer_norm import LayerNorm
 from .positionwise_feed_forward import PositionwiseFeedForward
 from .repeat import MultiSequential, repeat
+from .scorers_ctc import CTCPrefixScorer
+from .transformer_decoder import TransformerDecoder
 
 # north_star spelling
 Encoder = ConformerEncoder
 
 __all__ = ["ConformerEncoder", "Encoder", "EncoderLayer", "ConvolutionModule", "RelPositionMultiHeadedAttention",
            "PositionwiseFeedForward", "LayerNorm", "RelPositionalEncoding", "MultiSequential", "repeat", "CTC",
-           "ProjEncoder"]
+           "ProjEncoder", "TransformerDecoder", "CTCPrefixScorer"]

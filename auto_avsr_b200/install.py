@@ -59,6 +59,37 @@ def install_head(model):
     return model
 
 
+def install_decoder(model):
+    """The attention decoder's scoring path and the CTC prefix scorer.  ``E2E`` builds its decoder from
+    a class it imports by name and ``E2E.scorers()`` builds the CTC scorer likewise (e2e_asr_conformer.py:13,17,41-47,58-59):
+    this re-homes the decoder of an existing ``E2E`` instance onto the drop-in (the very same ``Parameter`` objects) and
+    re-points the two names in the already-imported E2E module, so ``model.scorers()`` -- what
+    ``get_beam_search_decoder`` feeds to ``BatchBeamSearch`` (lightning.py:126-157) -- returns the B200 scorers.
+    Inference only: the teacher-forced ``decoder.forward`` of the training loss stays with the reference module, so call
+    this on a model that is used for decoding."""
+    from .espnet_dropin import scorer_interface, scorers_ctc
+    from .espnet_dropin import transformer_decoder as td
+
+    scorer_interface.rebind()
+    old = model.decoder
+    emb, first = old.embed[0], old.decoders[0]
+    new = td.TransformerDecoder(odim=emb.num_embeddings, attention_dim=emb.embedding_dim, attention_heads=first.self_attn.h,
+                                linear_units=first.feed_forward.w_1.out_features, num_blocks=len(old.decoders))
+    for name, p in old.named_parameters():
+        mod = new
+        *path, leaf = name.split(".")
+        for part in path:
+            mod = getattr(mod, part) if not part.isdigit() else mod[int(part)]
+        setattr(mod, leaf, p)
+    new.train(old.training)
+    model.decoder = new
+    e2e = sys.modules.get(E2E_MODULE)
+    if e2e is not None:
+        e2e.TransformerDecoder = td.TransformerDecoder
+        e2e.CTCPrefixScorer = scorers_ctc.CTCPrefixScorer
+    return model
+
+
 def is_installed() -> bool:
     mod = sys.modules.get(REF_ENCODER_MODULE)
     return mod is not None and mod.__name__.startswith("auto_avsr_b200")

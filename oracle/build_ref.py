@@ -26,6 +26,17 @@ FILES = [
     "espnet/nets/pytorch_backend/transformer/repeat.py",
     "espnet/nets/pytorch_backend/nets_utils.py",
     "espnet/nets/pytorch_backend/ctc.py",
+    # the attention decoder, the CTC prefix scorer and the beam search that drives them
+    "espnet/nets/pytorch_backend/decoder/transformer_decoder.py",
+    "espnet/nets/pytorch_backend/transformer/mask.py",
+    "espnet/nets/scorer_interface.py",
+    "espnet/nets/scorers/__init__.py",
+    "espnet/nets/scorers/ctc.py",
+    "espnet/nets/scorers/length_bonus.py",
+    "espnet/nets/ctc_prefix_score.py",
+    "espnet/nets/e2e_asr_common.py",
+    "espnet/nets/beam_search.py",
+    "espnet/nets/batch_beam_search.py",
 ]
 
 
@@ -60,6 +71,19 @@ def import_reference_encoder():
         raise ImportError(f"another espnet is already imported ({ce.__file__}); import the reference copy first")
     ConformerEncoder = ce.ConformerEncoder
     return ConformerEncoder, make_non_pad_mask
+
+
+def import_reference_search():
+    """-> dict of the reference copy's decoding classes (TransformerDecoder, CTC, CTCPrefixScorer, LengthBonus,
+    BatchBeamSearch); raises ImportError if oracle/_ref was not built."""
+    import_reference_encoder()
+    from espnet.nets.batch_beam_search import BatchBeamSearch
+    from espnet.nets.pytorch_backend.ctc import CTC
+    from espnet.nets.pytorch_backend.decoder.transformer_decoder import TransformerDecoder
+    from espnet.nets.scorers.ctc import CTCPrefixScorer
+    from espnet.nets.scorers.length_bonus import LengthBonus
+    return dict(TransformerDecoder=TransformerDecoder, CTC=CTC, CTCPrefixScorer=CTCPrefixScorer, LengthBonus=LengthBonus,
+                BatchBeamSearch=BatchBeamSearch)
 
 
 if __name__ == "__main__":

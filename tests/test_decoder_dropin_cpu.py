@@ -1,0 +1,178 @@
+"""Host logic of row 8f #3 on the CPU: the TransformerDecoder / CTCPrefixScorer drop-ins and the device beam loop keep
+the reference's surface (state-dict keys, scorer API, n-best of the search) -- driven through tests/emu's host replay of
+the library schedule, against the reference-generated fixtures; and the reference's OWN BatchBeamSearch (oracle/_ref,
+unmodified) drives the drop-in scorers to the same n-best.  The product path refuses CPU tensors."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import load_decoder_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_COPY = os.path.join(ROOT, "oracle", "_ref")
+HAVE_NVCC = os.path.exists("/usr/local/cuda/bin/nvcc")
+needs_emu = pytest.mark.skipif(not HAVE_NVCC, reason="nvcc is needed to build the host replay")
+
+
+class CpuCTC(torch.nn.Module):
+    """stands in for the CTC module in front of the prefix scorer in the emulated runs (ctc.py:77-84)"""
+
+    def __init__(self, head_sd):
+        super().__init__()
+        w, b = head_sd["ctc.ctc_lo.weight"], head_sd["ctc.ctc_lo.bias"]
+        self.ctc_lo = torch.nn.Linear(w.shape[1], w.shape[0])
+        self.ctc_lo.load_state_dict({"weight": w, "bias": b})
+
+    @torch.no_grad()
+    def log_softmax(self, hs):
+        return torch.log_softmax(self.ctc_lo(hs), dim=-1)
+
+
+def _dropin_decoder(c, lib=None):
+    from auto_avsr_b200 import TransformerDecoder
+    cfg = c["cfg"]
+    dec = TransformerDecoder(cfg["odim"], cfg["d_model"], cfg["n_heads"], cfg["linear_units"], cfg["num_blocks"])
+    dec.load_state_dict(c["dec_sd"], strict=True)
+    dec.eval()
+    dec.precision = "fp32"
+    dec._lib = lib
+    return dec
+
+
+def test_decoder_dropin_state_dict_contract_and_cpu_refusal():
+    from auto_avsr_b200 import CTCPrefixScorer, TransformerDecoder
+    from auto_avsr_b200.synthetic import decoder_state_dict
+    dec = TransformerDecoder(odim=5049, attention_dim=768, attention_heads=12, linear_units=3072, num_blocks=6)   # e2e_asr_conformer.py:41-47
+    sd = decoder_state_dict(0)
+    assert list(dec.state_dict().keys()) == list(sd.keys())
+    assert len(sd) == 6 * 26 + 5 and sum(v.numel() for v in sd.values()) == sum(p.numel() for p in dec.parameters())
+    dec.load_state_dict(sd, strict=True)
+    # the pre-3d422f6 spelling of after_norm is renamed on load (transformer_decoder.py:143-156)
+    old = {k.replace("after_norm.", "output_norm."): v for k, v in sd.items()}
+    dec.load_state_dict(old, strict=True)
+    dec.eval()
+    ys = torch.tensor([[5048]])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec.batch_score(ys, [None], torch.zeros(1, 7, 768))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec.score(ys[0], None, torch.zeros(7, 768))
+    for call in (lambda: dec(ys, None, torch.zeros(1, 7, 768), None), lambda: dec.forward_one_step(ys, None, torch.zeros(1, 7, 768))):
+        with pytest.raises(NotImplementedError):
+            call()
+    dec.train()
+    with pytest.raises(NotImplementedError, match="inference"):
+        dec.batch_score(ys, [None], torch.zeros(1, 7, 768))
+    with pytest.raises(NotImplementedError):
+        TransformerDecoder(10, 64, 1, 64, 1, concat_after=True)
+    sc = CTCPrefixScorer(torch.nn.Identity(), 9)
+    assert sc.select_state(None, 0) is None and sc.select_state([1, 2, 3], 1) == 2
+    with pytest.raises(RuntimeError, match="before batch_init_state"):
+        sc.batch_score_partial(torch.zeros(1, 1, dtype=torch.long), torch.zeros(1, 2, dtype=torch.long), [None], None)
+    with pytest.raises(NotImplementedError):
+        sc.init_state(torch.zeros(3, 4))
+
+
+def _check_nbest(nbest, z, tag, tol):
+    """same hypotheses in the same order as the reference's n-best (fixture keeps the first 10), scores within tol"""
+    assert len(nbest) == int(z[f"nbest_count_{tag}"])
+    for i in range(len(z[f"nbest_len_{tag}"])):
+        L = int(z[f"nbest_len_{tag}"][i])
+        h = nbest[i]
+        assert h["yseq"] == z[f"nbest_yseq_{tag}"][i, :L].tolist(), i
+        assert abs(h["score"] - float(z[f"nbest_score_{tag}"][i])) < tol
+        assert abs(h["scores"]["decoder"] - float(z[f"nbest_dec_{tag}"][i])) < tol
+        assert abs(h["scores"]["ctc"] - float(z[f"nbest_ctc_{tag}"][i])) < tol
+
+
+@needs_emu
+def test_device_beam_search_reproduces_the_reference_nbest_on_the_host_replay():
+    from auto_avsr_b200.beam_search import DeviceBeamSearch
+    from emu import build
+    c = load_decoder_case("decoder_tiny")
+    cfg = c["cfg"]
+    dec = _dropin_decoder(c, build.load())
+    bs = DeviceBeamSearch(dec, CpuCTC(c["head_sd"]), beam_size=cfg["beam"], vocab_size=cfg["odim"])
+    nbest = [h.asdict() for h in bs(c["memory"])]
+    _check_nbest(nbest, c["z"], "f32", 2e-3)
+    assert bs.stats["utterances"] == 1 and dec.engine().stats["begin"] == 1
+    assert dec.engine().stats["step"] == bs.stats["steps"] <= cfg["T"]
+    # a second utterance re-uses the prepared weights and the session
+    nbest2 = [h.asdict() for h in bs(c["memory"])]
+    assert [h["yseq"] for h in nbest2] == [h["yseq"] for h in nbest]
+    assert dec.engine().stats["prepare"] == 1 and dec.engine().stats["begin"] == 2
+    # no CTC scorer (ctc_weight 0): pure attention-decoder search still terminates with <eos>-closed hypotheses
+    plain = DeviceBeamSearch(dec, None, beam_size=3, vocab_size=cfg["odim"], ctc_weight=0.0)(c["memory"][:6])
+    assert plain and all(int(h.yseq[-1]) == cfg["odim"] - 1 for h in plain)
+
+
+@needs_emu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_COPY, "espnet")), reason="oracle/_ref not built")
+def test_reference_batch_beam_search_drives_the_dropin_scorers():
+    """The UNMODIFIED reference BatchBeamSearch (oracle/_ref copy), configured like get_beam_search_decoder
+    (lightning.py:126-157), with the drop-in TransformerDecoder + CTCPrefixScorer as its scorers."""
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, "tests")!r})
+from oracle import build_ref
+ref = build_ref.import_reference_search()
+import torch
+from helpers import load_decoder_case
+from test_decoder_dropin_cpu import CpuCTC, _dropin_decoder, _check_nbest
+from auto_avsr_b200 import CTCPrefixScorer, TransformerDecoder
+from auto_avsr_b200.espnet_dropin import scorer_interface
+from espnet.nets.scorer_interface import BatchPartialScorerInterface, BatchScorerInterface
+assert scorer_interface.rebind()
+assert issubclass(TransformerDecoder, BatchScorerInterface) and issubclass(CTCPrefixScorer, BatchPartialScorerInterface)
+from emu import build
+c = load_decoder_case("decoder_tiny")
+cfg = c["cfg"]
+lib = build.load()
+dec = _dropin_decoder(c, lib)
+ctc = CTCPrefixScorer(CpuCTC(c["head_sd"]), cfg["odim"] - 1)
+ctc._lib = lib
+token_list = [str(i) for i in range(cfg["odim"])]
+scorers = dict(decoder=dec, ctc=ctc, lm=None, length_bonus=ref["LengthBonus"](len(token_list)))
+weights = dict(decoder=0.9, ctc=0.1, lm=0.0, length_bonus=0)
+bs = ref["BatchBeamSearch"](beam_size=cfg["beam"], vocab_size=len(token_list), weights=weights, scorers=scorers,
+                            sos=cfg["odim"] - 1, eos=cfg["odim"] - 1, token_list=token_list, pre_beam_score_key="decoder")
+with torch.no_grad():
+    nbest = [h.asdict() for h in bs(c["memory"])]
+_check_nbest(nbest, c["z"], "f32", 2e-3)
+print("OK", len(nbest), dec.engine().stats)
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_COPY, "espnet")), reason="oracle/_ref not built")
+def test_install_decoder_rehomes_the_reference_decoder():
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+from oracle import build_ref
+ref = build_ref.import_reference_search()
+import torch
+import auto_avsr_b200
+
+class Shell(torch.nn.Module):          # the members of E2E the decoding path touches (e2e_asr_conformer.py:41-59)
+    def __init__(self):
+        super().__init__()
+        self.decoder = ref["TransformerDecoder"](odim=37, attention_dim=128, attention_heads=2, linear_units=256, num_blocks=2)
+        self.ctc = ref["CTC"](37, 128, 0.1, reduce=True)
+
+m = Shell().eval()
+before = {{k: v.data_ptr() for k, v in m.state_dict().items()}}
+params = {{id(p) for p in m.parameters()}}
+auto_avsr_b200.install_decoder(m)
+assert type(m.decoder).__module__ == "auto_avsr_b200.espnet_dropin.transformer_decoder"
+assert {{k: v.data_ptr() for k, v in m.state_dict().items()}} == before
+assert params == {{id(p) for p in m.parameters()}} and not m.decoder.training
+from espnet.nets.scorer_interface import BatchScorerInterface
+assert isinstance(m.decoder, BatchScorerInterface)
+print("OK")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr[-2000:]
