@@ -4,7 +4,7 @@
 // replay the CPU tests build (tests/emu/decoder_emu.cu: the same schedule and the same functors as plain loops --
 // test infrastructure, never loaded by the package).
 //
-// What it replaces in the reference (paths relative to /root/reference):
+// What it replaces in the reference (paths relative to the reference tree):
 //   TransformerDecoder.forward_one_step / batch_score  espnet/nets/pytorch_backend/decoder/transformer_decoder.py:260-334
 //   DecoderLayer.forward (pre-norm, cache)              transformer_decoder.py:63-140
 //   CTCPrefixScoreTH.__call__                           espnet/nets/ctc_prefix_score.py:72-200
@@ -356,8 +356,18 @@ int begin_body(BK& bk, const AvsrDecoderConfig& c, const DecPrep& P, const DecSe
     AVSR_TRY(bk.for_each((long)T * D, ConvertElem{memory, S.mem_op, dec_operand_kind(prec)}));
     a = S.mem_op;
   }
+  // Row chunks of <= 192 frames: every launch stays in the M < 256 regime of the persistent one-CTA GEMM -- the same
+  // kernel variant (fp32 output + bias) every step GEMM of this path uses; once per utterance, so the extra launches
+  // do not matter.
+  const size_t esz = prec == AVSR_PREC_F16 ? 2 : 4;
+  constexpr int kChunk = 192;
   for (int l = 0; l < c.num_blocks; ++l)
-    AVSR_TRY(bk.gemm(prec, a, P.L[l].src_kv_w, T, 2 * D, D, P.L[l].src_kv_b, S.mem_kv + (size_t)l * T * 2 * D, nullptr, 0.f, 0, 0));
+    for (int r0 = 0; r0 < T; r0 += kChunk) {
+      const int rows = T - r0 < kChunk ? T - r0 : kChunk;
+      const void* a_rows = reinterpret_cast<const char*>(a) + (size_t)r0 * D * esz;
+      AVSR_TRY(bk.gemm(prec, a_rows, P.L[l].src_kv_w, rows, 2 * D, D, P.L[l].src_kv_b,
+                       S.mem_kv + ((size_t)l * T + r0) * 2 * D, nullptr, 0.f, 0, 0));
+    }
   return AVSR_OK;
 }
 

@@ -468,6 +468,20 @@ def extras(dev, enc, args, peaks):
         out["gpu_eager_baseline"] = eager
     except Exception as e:          # noqa: BLE001
         out["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    # BASELINE.json configs[4] flavour: beam-search decoding of one utterance on the drop-in scorers vs
+    # the unmodified reference on the same GPU.  Runs LAST and in a CHILD process with its own CUDA context and timeout
+    # (scripts/bench_decode.py): whatever happens there cannot touch the headline measurement above.
+    try:
+        import subprocess
+        torch.cuda.synchronize()
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_decode.py"), "100", "40"], capture_output=True,
+                           text=True, timeout=300, cwd=ROOT)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("DECODE-JSON ")]
+        out["decode_beam_search"] = json.loads(rows[-1][len("DECODE-JSON "):]) if rows else \
+            {"error": f"child rc={r.returncode}: {(r.stderr or r.stdout)[-400:]}"}
+        log("extras: decode child done")
+    except Exception as e:          # noqa: BLE001
+        out["decode_beam_search"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

@@ -186,3 +186,17 @@ def test_emu_ctc_prefix_against_oracle_random(emu):
             r32, s32 = eng.select(r, log_psi, cand.to(torch.int32), torch.arange(n, dtype=torch.int32),
                                   torch.tensor(keep, dtype=torch.int32))
             last = keep
+
+
+def test_emu_decoder_long_memory_is_projected_in_row_chunks(emu):
+    """T > 192: avsr_decoder_begin projects the source K|V in row chunks; every frame must land in its row."""
+    c = load_decoder_case("decoder_tiny")
+    cfg = c["cfg"]
+    eng, params = _engine(c, emu)
+    g = torch.Generator().manual_seed(21)
+    mem = torch.randn(401, cfg["d_model"], generator=g)
+    eng.begin(params, mem, max_hyps=2, max_steps=2, precision="fp32")
+    sos = cfg["odim"] - 1
+    logp = eng.step(torch.tensor([sos, sos], dtype=torch.int32), None, 0)
+    ref = DO.decoder_logp(c["dec_sd"], torch.tensor([[sos], [sos]]), mem.double(), cfg["n_heads"])
+    assert err_stats(logp, ref)[0] < 2e-4
