@@ -2,7 +2,7 @@
 slot / ancestor addressing and every per-element functor of csrc/decoder_body.cuh are compiled against the host backend
 of tests/emu (same source, plain loops, naive fp32 GEMM / LayerNorm / log-softmax in place of the GPU-verified
 launchers) and driven through the package's own host code (auto_avsr_b200.decoder) with the SAME ctypes signatures.
-Compared with the reference-generated fixtures and the oracle.  The GPU parity proper is tests/test_zz_gpu_decoder.py."""
+Compared with the reference-generated fixtures and the oracle.  The GPU parity proper is tests/test_zzz_gpu_decoder.py."""
 import shutil
 
 import pytest

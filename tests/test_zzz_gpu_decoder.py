@@ -179,7 +179,7 @@ from oracle import build_ref
 ref = build_ref.import_reference_search()
 import torch
 from helpers import load_decoder_case
-from test_zz_gpu_decoder import _decoder, _ctc, _compare_nbest
+from test_zzz_gpu_decoder import _decoder, _ctc, _compare_nbest
 from auto_avsr_b200 import CTCPrefixScorer
 from auto_avsr_b200.espnet_dropin import scorer_interface
 assert scorer_interface.rebind()
