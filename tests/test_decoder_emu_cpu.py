@@ -56,8 +56,9 @@ def test_product_engine_refuses_cpu_tensors():
         CtcPrefixEngine(torch.zeros(5, 7), 0, 6)
 
 
-def test_emu_decoder_steps_match_reference_fixture(emu):
-    c = load_decoder_case("decoder_tiny")
+@pytest.mark.parametrize("name", ["decoder_tiny", "decoder_full"])
+def test_emu_decoder_steps_match_reference_fixture(emu, name):
+    c = load_decoder_case(name)
     z, cfg = c["z"], c["cfg"]
     eng, params = _engine(c, emu)
     n = cfg["n_hyp"]
