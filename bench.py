@@ -475,7 +475,7 @@ def extras(dev, enc, args, peaks):
         import subprocess
         torch.cuda.synchronize()
         r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_decode.py"), "100", "40"], capture_output=True,
-                           text=True, timeout=300, cwd=ROOT)
+                           text=True, timeout=150, cwd=ROOT)
         rows = [ln for ln in r.stdout.splitlines() if ln.startswith("DECODE-JSON ")]
         out["decode_beam_search"] = json.loads(rows[-1][len("DECODE-JSON "):]) if rows else \
             {"error": f"child rc={r.returncode}: {(r.stderr or r.stdout)[-400:]}"}
