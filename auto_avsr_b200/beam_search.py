@@ -155,3 +155,36 @@ class DeviceBeamSearch:
             return [] if minlenratio < 0.1 else self.forward(x, maxlenratio, max(0.0, minlenratio - 0.1))
         return [Hypothesis(yseq=h["yseq"], score=h["score"], scores={"decoder": h["decoder"], "ctc": h["ctc"]})
                 for h in nbest]
+
+
+def shard_utterances(lengths, world: int) -> List[List[int]]:
+    """Which utterances each rank decodes (decoding shards by utterance, no exchange on the data path).
+    Search cost grows like T * steps ~ T^2, so: longest first onto the least-loaded rank (LPT), ties to the lower rank;
+    each rank's list is returned in corpus order.  Deterministic on every rank (no communication)."""
+    load = [0] * world
+    owner: List[List[int]] = [[] for _ in range(world)]
+    for idx in sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[r].append(idx)
+        load[r] += int(lengths[idx]) ** 2
+    return [sorted(o) for o in owner]
+
+
+def decode_sharded(search, utterances, rank: int = 0, world: int = 1, gather: bool = True):
+    """Decode a corpus data-parallel: rank r runs `search` (a DeviceBeamSearch, or the reference's BatchBeamSearch over the
+    drop-in scorers) on its share of `utterances` (list of (T_i, d) encoder outputs on that rank's device); the only
+    exchange is the host-side gather of the n-best lists at the end (``torch.distributed.all_gather_object``).
+    -> list over the corpus of n-best lists (dicts as ``Hypothesis.asdict()``); with gather=False only this rank's entries
+    are filled (others None)."""
+    mine = shard_utterances([u.shape[0] for u in utterances], world)[rank]
+    out: List[Optional[list]] = [None] * len(utterances)
+    for i in mine:
+        out[i] = [h.asdict() for h in search(utterances[i])]
+    if world > 1 and gather:
+        import torch.distributed as dist
+        parts: List[Optional[list]] = [None] * world
+        dist.all_gather_object(parts, {i: out[i] for i in mine})
+        for part in parts:
+            for i, nbest in part.items():
+                out[i] = nbest
+    return out
