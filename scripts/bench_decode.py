@@ -37,7 +37,15 @@ def main():
     from auto_avsr_b200.espnet_dropin import scorer_interface
     from auto_avsr_b200.synthetic import decoder_state_dict, encoder_input, head_state_dict
 
-    dev = torch.device("cuda:0")
+    # AVSR_BENCH_DECODE_DRYRUN=1: CPU dry run of THIS SCRIPT's plumbing on the tests' host replay (no measurement value)
+    dry = os.environ.get("AVSR_BENCH_DECODE_DRYRUN") == "1"
+    dev = torch.device("cpu" if dry else "cuda:0")
+    lib = None
+    if dry:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from emu import build as emu_build
+        lib = emu_build.load()
+    sync = (lambda: None) if dry else torch.cuda.synchronize
     dsd, hsd = decoder_state_dict(4), head_state_dict(4)
     ctc_sd = {"ctc_lo.weight": hsd["ctc.ctc_lo.weight"], "ctc_lo.bias": hsd["ctc.ctc_lo.bias"]}
     x = encoder_input([T], 768, 9)[0].to(dev)
@@ -45,11 +53,11 @@ def main():
 
     def timed(fn, reps):
         fn()                                                  # warm-up (weight preparation, allocations)
-        torch.cuda.synchronize()
+        sync()
         t0 = time.perf_counter()
         for _ in range(reps):
             res = fn()
-        torch.cuda.synchronize()
+        sync()
         return (time.perf_counter() - t0) / reps, res
 
     dec = TransformerDecoder(odim=odim, attention_dim=768, attention_heads=12, linear_units=3072, num_blocks=6)
@@ -57,6 +65,17 @@ def main():
     ctc = CTC(odim, 768, 0.1)
     ctc.load_state_dict(ctc_sd)
     dec, ctc = dec.to(dev).eval(), ctc.to(dev).eval()
+    if dry:
+        class _CpuCTC(torch.nn.Module):                       # the drop-in CTC refuses CPU tensors
+            def __init__(self, lo):
+                super().__init__()
+                self.ctc_lo = lo
+
+            @torch.no_grad()
+            def log_softmax(self, hs):
+                return torch.log_softmax(self.ctc_lo(hs), dim=-1)
+        ctc = _CpuCTC(ctc.ctc_lo)
+        dec._lib, dec.precision = lib, "fp32"
     best = {}
     try:
         bs = DeviceBeamSearch(dec, ctc, beam_size=beam)
@@ -80,7 +99,9 @@ def main():
                                           sos=eos, eos=eos, token_list=token_list, pre_beam_score_key="decoder")
         try:
             scorer_interface.rebind()
-            bs2 = build(dec, CTCPrefixScorer(ctc, eos))
+            scorer = CTCPrefixScorer(ctc, eos)
+            scorer._lib = lib
+            bs2 = build(dec, scorer)
             with torch.no_grad():
                 dt, nb = timed(lambda: bs2(x), 2)
             best["ref_loop"] = (nb[0].yseq.tolist(), float(nb[0].score))

@@ -176,3 +176,24 @@ print("OK")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+@needs_emu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_COPY, "espnet")), reason="oracle/_ref not built")
+def test_bench_decode_child_dry_run_agrees_with_the_reference_decoder():
+    """scripts/bench_decode.py (the child bench.py's extras start) on the CPU: full-size decoder (d 768, 6 layers, odim 5049),
+    the drop-in scorers on the host replay under DeviceBeamSearch AND under the reference's BatchBeamSearch, next to the
+    reference's own decoder + CTCPrefixScorer: one best hypothesis, one score."""
+    import json
+    env = dict(os.environ, AVSR_BENCH_DECODE_DRYRUN="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_decode.py"), "6", "4"], capture_output=True, text=True,
+                       timeout=600, env=env, cwd=ROOT)
+    rows = [ln for ln in r.stdout.splitlines() if ln.startswith("DECODE-JSON ")]
+    assert r.returncode == 0 and rows, r.stdout[-1000:] + r.stderr[-2000:]
+    out = json.loads(rows[-1][len("DECODE-JSON "):])
+    for arm in ("device_beam_search", "reference_loop_dropins", "reference_eager"):
+        assert "error" not in out[arm], out[arm]
+    assert out["same_best_hypothesis_as_reference_eager"] is True
+    assert out["best_score_gap_vs_reference_eager"] < 1e-3
+    assert abs(out["reference_loop_dropins"]["best_score"] - out["device_beam_search"]["best_score"]) < 1e-4
+    assert out["device_beam_search"]["steps"] == 6
