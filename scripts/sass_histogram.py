@@ -15,7 +15,9 @@ WANT = [r"attention_f16_kernel", r"gemm_tc2_kernelILi0ELi384ELb1ELb0ELb1E", r"ge
         r"gemm_tc2_kernelILi0ELi128ELb0ELb1ELb1E", r"gemm_tc2_kernelILi1ELi256", r"gemm_tc2_kernelILi3ELi256",
         r"gemm_tc2_kernelILi5ELi512", r"gemm_tc_kernelILi4ELi256ELi2E6__half", r"ln_kernelILi0ELb0ELi2ELi4ELi3E",
         r"ln_kernelILi3ELb1ELi2ELi4ELi3E", r"dwconv_bn_silu_kernelILi31E"]
-KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "MUFU", "FSEL", "HMMA", "LDG", "STG"]
+if len(sys.argv) > 1:          # patterns on the command line replace the default kernel list
+    WANT = sys.argv[1:]
+KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "MUFU", "FSEL", "HMMA", "FFMA", "LDG", "STG"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 cur, funcs = None, collections.OrderedDict()
