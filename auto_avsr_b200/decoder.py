@@ -13,7 +13,7 @@ Reference being replaced: TransformerDecoder.batch_score / forward_one_step
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
