@@ -197,3 +197,31 @@ def test_bench_decode_child_dry_run_agrees_with_the_reference_decoder():
     assert out["best_score_gap_vs_reference_eager"] < 1e-3
     assert abs(out["reference_loop_dropins"]["best_score"] - out["device_beam_search"]["best_score"]) < 1e-4
     assert out["device_beam_search"]["steps"] == 6
+
+
+@needs_emu
+def test_shim_replays_test_step_through_the_beam_search():
+    """lightning.py:69-76 (after the front-end) on an E2EShell whose encoder side is stubbed out (it needs the GPU; its own
+    replay is tests/test_gpu_callers.py): proj_encoder -> encoder(x, None) -> beam search over model.scorers() -> token ids."""
+    from auto_avsr_b200 import shim
+    from auto_avsr_b200.beam_search import DeviceBeamSearch
+    from emu import build
+    c = load_decoder_case("decoder_tiny")
+    cfg = c["cfg"]
+    model = shim.E2EShell(odim=cfg["odim"], idim=cfg["d_model"], adim=cfg["d_model"], aheads=cfg["n_heads"], eunits=cfg["linear_units"],
+                          elayers=1)
+    assert set(model.scorers()) == {"decoder", "ctc"} and model.eos == cfg["odim"] - 1
+    # the tiny fixture's decoder has 2 layers: swap the shell's 6-layer decoder for it, stub the encoder side
+    model.decoder = _dropin_decoder(c, build.load())
+    model.ctc = CpuCTC(c["head_sd"])
+    model.proj_encoder = torch.nn.Identity()
+    class _PassThrough(torch.nn.Module):
+        def forward(self, x, masks):
+            return x, masks
+    model.encoder = _PassThrough()
+    bs = shim.get_beam_search_decoder(model, beam_size=cfg["beam"])
+    assert isinstance(bs, DeviceBeamSearch) and bs.weights == {"decoder": 0.9, "ctc": 0.1} and bs.pre_beam_size == 7
+    ids = shim.test_step_decode(model, c["memory"], bs)
+    z = c["z"]
+    L = int(z["nbest_len_f32"][0])
+    assert ids.tolist() == z["nbest_yseq_f32"][0, 1:L].tolist()            # best hypothesis of the reference, <sos> dropped
