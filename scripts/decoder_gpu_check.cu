@@ -30,6 +30,7 @@
 
 struct Arr { int dtype; std::vector<long long> shape; std::vector<char> data; size_t count() const { size_t n = 1; for (auto s : shape) n *= s; return n; } };
 static std::map<std::string, Arr> g_blob;
+static bool g_time = false;      // --time: after the parity pass, replay the last (widest) step / CTC call under CUDA events
 
 static void load_blob(const char* path) {
   FILE* f = fopen(path, "rb");
@@ -146,6 +147,20 @@ static double run_decoder_case(const char* tag, bool hashed_weights, int precisi
     for (int i = 0; i < (int)O; ++i) sum += exp((double)got[i]);
     printf("  %s prec=%d step %d n=%d  max|logp - oracle| = %.3e   sum(exp(row0)) = %.6f\n", tag, precision, s, n, mx, sum);
     worst = mx > worst ? mx : worst;
+    if (g_time && s == steps - 1) {
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      const unsigned long long l0 = avsr_launch_count();
+      for (int it = 0; it < 5; ++it)
+        AV(avsr_decoder_step(&cfg, prepared, session, sb, T, max_steps, max_hyps, d_tok, d_anc, s, n, d_logp, work, wb, precision, nullptr));
+      const int reps = 50;
+      CK(cudaEventRecord(e0));
+      for (int it = 0; it < reps; ++it)
+        AV(avsr_decoder_step(&cfg, prepared, session, sb, T, max_steps, max_hyps, d_tok, d_anc, s, n, d_logp, work, wb, precision, nullptr));
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+      printf("  TIMING %s prec=%d: avsr_decoder_step n=%d step=%d T=%d: %.1f us per call (CUDA events over %d back-to-back calls, %llu launches per call)\n",
+             tag, precision, n, s, T, ms * 1e3 / reps, reps, (avsr_launch_count() - l0) / (reps + 5));
+    }
   }
   return worst;
 }
@@ -194,8 +209,46 @@ static double run_ctc_case() {
   return worst;
 }
 
+static void time_ctc(int T, int O, int n, int S) {
+  std::vector<float> h((size_t)T * O);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = -8.5f + 0.001f * (float)(i % 977);        // plausible log-posteriors
+  float* logp = (float*)to_dev(h.data(), h.size() * 4);
+  std::vector<int32_t> cand((size_t)n * S), last(n, O - 1);
+  for (int i = 0; i < n; ++i) for (int c = 0; c < S; ++c) cand[(size_t)i * S + c] = 1 + ((i * 131 + c * 17) % (O - 2));
+  int32_t* d_cand = (int32_t*)to_dev(cand.data(), cand.size() * 4);
+  int32_t* d_last = (int32_t*)to_dev(last.data(), n * 4);
+  float *r_prev, *s_prev, *local, *r, *log_psi;
+  CK(cudaMalloc(&r_prev, (size_t)T * 2 * n * 4)); CK(cudaMemset(r_prev, 0, (size_t)T * 2 * n * 4));
+  CK(cudaMalloc(&s_prev, n * 4)); CK(cudaMemset(s_prev, 0, n * 4));
+  CK(cudaMalloc(&local, (size_t)n * O * 4)); CK(cudaMalloc(&log_psi, (size_t)n * O * 4)); CK(cudaMalloc(&r, (size_t)T * 2 * n * S * 4));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int it = 0; it < 3; ++it) AV(avsr_ctc_prefix_score(logp, T, O, 0, O - 1, 5, d_last, r_prev, s_prev, d_cand, n, S, local, r, log_psi, nullptr));
+  const int reps = 50;
+  CK(cudaEventRecord(e0));
+  for (int it = 0; it < reps; ++it) AV(avsr_ctc_prefix_score(logp, T, O, 0, O - 1, 5, d_last, r_prev, s_prev, d_cand, n, S, local, r, log_psi, nullptr));
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("  TIMING avsr_ctc_prefix_score T=%d O=%d n=%d S=%d: %.1f us per call\n", T, O, n, S, ms * 1e3 / reps);
+}
+
 int main(int argc, char** argv) {
-  load_blob(argc > 1 ? argv[1] : "scripts/bin/decoder_check.blob");
+  const char* blob = "scripts/bin/decoder_check.blob";
+  bool only_time = false;
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "--time")) g_time = true;
+    else if (!strcmp(argv[i], "--only-time")) g_time = only_time = true;
+    else blob = argv[i];
+  }
+  load_blob(blob);
+  if (only_time) {            // the two full-size decoder passes (they carry the timing hook) and the CTC call, nothing else
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    printf("device: %s\n", p.name);
+    run_decoder_case("full", true, AVSR_PREC_F16);
+    run_decoder_case("full", true, AVSR_PREC_FP32);
+    time_ctc(100, 5049, 40, 60);
+    time_ctc(400, 5049, 40, 60);
+    return 0;
+  }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s (sm_%d%d), libavsr ABI %d\n", prop.name, prop.major, prop.minor, avsr_abi_version());
   int bad = 0;
