@@ -225,3 +225,39 @@ def test_shim_replays_test_step_through_the_beam_search():
     z = c["z"]
     L = int(z["nbest_len_f32"][0])
     assert ids.tolist() == z["nbest_yseq_f32"][0, 1:L].tolist()            # best hypothesis of the reference, <sos> dropped
+
+
+@needs_emu
+@pytest.mark.parametrize("T,beam,odim,seed", [(1, 3, 11, 0), (2, 1, 9, 1), (5, 4, 8, 2), (9, 6, 23, 3), (14, 2, 37, 4), (7, 5, 6, 5)])
+def test_device_beam_search_corner_shapes_against_the_oracle_loop(T, beam, odim, seed):
+    """Corner shapes of the search (T = 1: the first step is also the last; beam 1; pre-beam >= vocabulary -> no pre-beam;
+    vocabularies so small that hypotheses end early and the beam runs dry) against the oracle's restatement of
+    BatchBeamSearch, on a random 1-layer decoder through the host replay."""
+    from auto_avsr_b200 import TransformerDecoder
+    from auto_avsr_b200.beam_search import DeviceBeamSearch
+    from auto_avsr_b200.synthetic import decoder_state_dict, encoder_input, head_state_dict
+    from emu import build
+    from oracle import decoder_oracle as DO
+    from oracle import head_oracle as HO
+    d, H, ff = 64, 1, 64
+    sd = decoder_state_dict(100 + seed, odim, d, H, ff, 1)
+    hsd = head_state_dict(100 + seed, 64, d, odim)
+    mem = encoder_input([T], d, 200 + seed)[0]
+    dec = TransformerDecoder(odim, d, H, ff, 1)
+    dec.load_state_dict(sd, strict=True)
+    dec.eval()
+    dec.precision, dec._lib = "fp32", build.load()
+    got = [h.asdict() for h in DeviceBeamSearch(dec, CpuCTC(hsd), beam_size=beam, vocab_size=odim)(mem)]
+    want = DO.beam_search(lambda ys: DO.decoder_logp(sd, ys, mem.double(), H), HO.ctc_log_softmax(mem.double(), hsd), odim, beam,
+                          maxlen=T)
+    assert len(got) == len(want) >= 1
+    assert got[0]["yseq"] == want[0]["yseq"] and got[0]["yseq"][0] == got[0]["yseq"][-1] == odim - 1
+    assert abs(got[0]["score"] - want[0]["score"]) < 2e-3
+    # same multiset of ended hypotheses (order may swap between near-ties in fp32 vs fp64)
+    key = lambda h: tuple(h["yseq"])            # noqa: E731
+    assert sorted(map(key, got)) == sorted(map(key, want))
+    by = {key(h): h for h in want}
+    for h in got:
+        assert abs(h["score"] - by[key(h)]["score"]) < 2e-3
+        assert abs(h["scores"]["decoder"] - by[key(h)]["scores"]["decoder"]) < 2e-3
+        assert abs(h["scores"]["ctc"] - by[key(h)]["scores"]["ctc"]) < 2e-3
