@@ -182,6 +182,8 @@ def decode_sharded(search, utterances, rank: int = 0, world: int = 1, gather: bo
         out[i] = [h.asdict() for h in search(utterances[i])]
     if world > 1 and gather:
         import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("decode_sharded(world > 1, gather=True) needs an initialised torch.distributed process group")
         parts: List[Optional[list]] = [None] * world
         dist.all_gather_object(parts, {i: out[i] for i in mine})
         for part in parts:

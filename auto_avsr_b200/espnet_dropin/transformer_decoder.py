@@ -10,7 +10,8 @@ Same constructor signature, sub-module / parameter names and state-dict keys as 
 Scorer state: the reference hands the beam search, per hypothesis, the list of every layer's output over the prefix
 and re-projects K/V of the whole prefix -- and of the whole encoder memory -- at every step.  Here the K/V live in the
 library's per-utterance session (``auto_avsr_b200.decoder.DecoderEngine``); the state of a hypothesis is just the tuple
-of beam slots of its prefix positions, which the beam search's ``select_state`` (``state[i]``) shuffles for free."""
+(utterance serial, beam slot of prefix position 0, 1, ...), which the beam search's ``select_state`` (``state[i]``)
+shuffles for free.  One utterance at a time per decoder module (as the reference's CTCPrefixScorer.impl)."""
 from typing import Any, List, Optional, Tuple
 
 import torch
@@ -113,6 +114,7 @@ class TransformerDecoder(_si.BatchScorerInterface, torch.nn.Module):
         #: positions per session; None = memory length + 1 (BeamSearch.forward's maxlen with maxlenratio 0, + the <eos> step)
         self.max_steps: Optional[int] = None
         self._engine = None
+        self._utterance = 0         # serial of the utterance the session currently holds
         self._lib = None            # tests inject the host replay here; None = libavsr_b200
 
     # ---------------------------------------------------------------- engine
@@ -150,11 +152,18 @@ class TransformerDecoder(_si.BatchScorerInterface, torch.nn.Module):
             if step != 0:
                 raise ValueError("a hypothesis without a state must be the bare <sos> prefix")
             eng.begin(self, xs[0], max(self.beam_slots, n), self.max_steps, self.precision or default_precision())
+            self._utterance += 1
             anc = None
+            prev = [(self._utterance,)] * n
         else:
-            if any(len(s) != step for s in states):
+            # a state is (utterance serial, slot of position 0, slot of position 1, ...): the session holds ONE utterance,
+            # so states of an utterance another search has since replaced must not be scored against its K/V
+            if any(len(s) != step + 1 for s in states):
                 raise ValueError("batch_score: every hypothesis must have the same prefix length")
-            anc = torch.tensor(states, dtype=torch.int32).t().contiguous().to(ys.device)        # (step, n)
+            if any(s[0] != self._utterance for s in states):
+                raise ValueError("batch_score: these hypotheses belong to an utterance whose session was replaced "
+                                 "(one utterance at a time per decoder module)")
+            anc = torch.tensor([s[1:] for s in states], dtype=torch.int32).t().contiguous().to(ys.device)        # (step, n)
+            prev = states
         logp = eng.step(ys[:, -1].to(torch.int32), anc, step)
-        prev = states if states[0] is not None else [()] * n
         return logp, [tuple(prev[i]) + (i,) for i in range(n)]

@@ -261,3 +261,24 @@ def test_device_beam_search_corner_shapes_against_the_oracle_loop(T, beam, odim,
         assert abs(h["score"] - by[key(h)]["score"]) < 2e-3
         assert abs(h["scores"]["decoder"] - by[key(h)]["scores"]["decoder"]) < 2e-3
         assert abs(h["scores"]["ctc"] - by[key(h)]["scores"]["ctc"]) < 2e-3
+
+
+@needs_emu
+def test_decoder_refuses_states_of_a_replaced_utterance():
+    """The session holds one utterance: hypotheses of an earlier utterance must not be scored against the new K/V."""
+    from emu import build
+    c = load_decoder_case("decoder_tiny")
+    cfg = c["cfg"]
+    dec = _dropin_decoder(c, build.load())
+    sos = cfg["odim"] - 1
+    xs = c["memory"].unsqueeze(0)
+    _, st_a = dec.batch_score(torch.tensor([[sos]]), [None], xs)
+    _, st_a2 = dec.batch_score(torch.tensor([[sos, 3]]), st_a, xs)                 # same utterance: fine
+    assert st_a2[0][0] == st_a[0][0] and len(st_a2[0]) == 3
+    _, st_b = dec.batch_score(torch.tensor([[sos]]), [None], xs[:, :7])            # a new utterance replaces the session
+    assert st_b[0][0] == st_a[0][0] + 1
+    with pytest.raises(ValueError, match="session was replaced"):
+        dec.batch_score(torch.tensor([[sos, 3, 4]]), st_a2, xs)
+    with pytest.raises(ValueError, match="same prefix length"):
+        dec.batch_score(torch.tensor([[sos, 3, 4]]), st_b, xs[:, :7])
+    dec.batch_score(torch.tensor([[sos, 5]]), st_b, xs[:, :7])
