@@ -201,3 +201,19 @@ def test_emu_decoder_long_memory_is_projected_in_row_chunks(emu):
     logp = eng.step(torch.tensor([sos, sos], dtype=torch.int32), None, 0)
     ref = DO.decoder_logp(c["dec_sd"], torch.tensor([[sos], [sos]]), mem.double(), cfg["n_heads"])
     assert err_stats(logp, ref)[0] < 2e-4
+
+
+def test_emu_ctc_select_of_a_token_off_the_candidate_list(emu):
+    """A kept token that was not a candidate (only possible when fewer than `beam` candidates are live) carries logzero
+    forward variables and the logzero prefix score, like the reference's select_state on log_psi."""
+    from auto_avsr_b200.decoder import CtcPrefixEngine
+    g = torch.Generator().manual_seed(2)
+    logp = torch.log_softmax(torch.randn(6, 9, generator=g), -1)
+    eng = CtcPrefixEngine(logp, 0, 8, _lib=emu)
+    r0, s0 = eng.initial(2)
+    cand = torch.tensor([[1, 2, 3], [4, 5, 6]], dtype=torch.int32)
+    local, r, log_psi = eng.score(0, torch.tensor([8, 8], dtype=torch.int32), r0, s0, cand)
+    r_next, s_next = eng.select(r, log_psi, cand, torch.tensor([0, 1, 1], dtype=torch.int32), torch.tensor([2, 7, 5], dtype=torch.int32))
+    assert torch.equal(r_next[:, :, 0], r[:, :, 0, 1]) and torch.equal(r_next[:, :, 2], r[:, :, 1, 1])
+    assert (r_next[:, :, 1] == DO.LOGZERO).all() and float(s_next[1]) == DO.LOGZERO
+    assert float(s_next[0]) == float(log_psi[0, 2]) and float(s_next[2]) == float(log_psi[1, 5])
