@@ -217,3 +217,27 @@ def test_emu_ctc_select_of_a_token_off_the_candidate_list(emu):
     assert torch.equal(r_next[:, :, 0], r[:, :, 0, 1]) and torch.equal(r_next[:, :, 2], r[:, :, 1, 1])
     assert (r_next[:, :, 1] == DO.LOGZERO).all() and float(s_next[1]) == DO.LOGZERO
     assert float(s_next[0]) == float(log_psi[0, 2]) and float(s_next[2]) == float(log_psi[1, 5])
+
+
+@pytest.mark.parametrize("d,H,ff,L,odim", [(128, 4, 192, 1, 19), (192, 3, 64, 3, 70), (64, 1, 128, 2, 5)])
+def test_emu_decoder_other_geometries_against_oracle(emu, d, H, ff, L, odim):
+    """head sizes other than 64 (32, 64, 64 with 3 heads), odd layer counts, tiny vocabularies padded to 64 output rows"""
+    from auto_avsr_b200.decoder import DecoderEngine
+    from auto_avsr_b200.synthetic import decoder_state_dict, encoder_input
+    sd = decoder_state_dict(7, odim, d, H, ff, L)
+    mem = encoder_input([11], d, 8)[0]
+    eng = DecoderEngine(odim, d, H, ff, L, _lib=emu)
+    params = _Params(sd)
+    eng.begin(params, mem, max_hyps=3, max_steps=4, precision="fp32")
+    sos = odim - 1
+    prefixes, chains = [[sos], [sos], [sos]], [[], [], []]
+    eng.step(torch.tensor([sos] * 3, dtype=torch.int32), None, 0)
+    for step in range(1, 4):
+        toks = [(step * 3 + i) % (odim - 1) for i in range(3)]
+        parents = [(i + step) % 3 for i in range(3)]                   # the hypotheses change lanes every step
+        prefixes = [prefixes[p] + [t] for p, t in zip(parents, toks)]
+        chains = [chains[p] + [p] for p in parents]
+        anc = torch.tensor(chains, dtype=torch.int32).T.contiguous()
+        logp = eng.step(torch.tensor(toks, dtype=torch.int32), anc, step)
+        ref = DO.decoder_logp(sd, torch.tensor(prefixes), mem.double(), H)
+        assert err_stats(logp, ref)[0] < 2e-4, (step, d, H)
